@@ -1,0 +1,94 @@
+"""Context = one gnb_ctx (device workspace + repacked weights) bound to one CUDA device."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, fields
+from typing import Optional
+
+import numpy as np
+
+from . import _lib, weights as _weights
+
+
+@dataclass
+class Config:
+    """Python mirror of ``struct gnb_config``.  Defaults follow the reference's class constants
+    (ros/gisnav/gisnav/core/pose_node.py:60-72) where one exists."""
+
+    max_keypoints: int = 1024  # MAX_KEYPOINTS, pose_node.py:66
+    nms_radius: int = 4
+    keypoint_threshold: float = 0.005
+    border: int = 4
+    match_threshold: float = 0.5  # CONFIDENCE_THRESHOLD, pose_node.py:60
+    min_matches: int = 15  # MIN_MATCHES, pose_node.py:63
+    ransac_iters: int = 2048  # reference: iterationsCount=10 + early exit (_shared.py:115)
+    reproj_px: float = 8.0
+    ransac_seed: int = 0
+    refine: int = 1
+    max_batch: int = 8
+    max_image_h: int = 1088
+    max_image_w: int = 1280
+    conv_impl: int = 0  # 0 tcgen05 (product), 1 SIMT validation kernel
+    match_impl: int = 0
+
+    def to_c(self) -> _lib.GnbConfig:
+        c = _lib.GnbConfig()
+        for f in fields(self):
+            setattr(c, f.name, getattr(self, f.name))
+        return c
+
+
+class Context:
+    def __init__(self, config: Optional[Config] = None, weights: Optional[bytes] = None, device: int = 0,
+                 weights_device_ptr: Optional[int] = None, weights_nbytes: int = 0):
+        self._lib = _lib.load()
+        self.config = config or Config()
+        self.device = device
+        self._h = C.c_void_p()
+        cfg = self.config.to_c()
+        if weights_device_ptr is not None:
+            rc = self._lib.gnb_create(C.byref(cfg), C.c_void_p(weights_device_ptr), weights_nbytes, 1, device, C.byref(self._h))
+        else:
+            blob = weights if weights is not None else _weights.load()
+            buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+            rc = self._lib.gnb_create(C.byref(cfg), C.cast(buf, C.c_void_p), len(blob), 0, device, C.byref(self._h))
+        if rc != 0:
+            raise _lib.GnbError(rc, self._lib.gnb_last_error(None).decode())
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._h:
+            raise RuntimeError("context destroyed")
+        return self._h
+
+    def check(self, rc: int) -> int:
+        """Negative status => raise (usage/CUDA error); soft failures (>0) are returned."""
+        if rc < 0:
+            msg = self._lib.gnb_last_error(self._h).decode()
+            if rc == _lib.GNB_E_RANGE:
+                raise IndexError(msg)  # numpy raises IndexError at _shared.py:100-101
+            raise _lib.GnbError(rc, msg)
+        return rc
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gnb_launch_count(self._h))
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._lib.gnb_stream(self._h) or 0)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.gnb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ptr(a: Optional[np.ndarray]) -> Optional[C.c_void_p]:
+    return None if a is None else C.c_void_p(a.ctypes.data)

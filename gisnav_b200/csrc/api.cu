@@ -1,0 +1,528 @@
+// api.cu — C ABI of libgisnav_b200.so (include/gisnav_b200.h): context lifetime, workspace, the
+// three reference call sites (detectAndCompute / matcher / compute_pose), the fused batch path
+// and the stage-isolated hooks used by the parity tests.
+#include "common.cuh"
+
+#include <new>
+#include <vector>
+
+static char g_create_err[512] = "";
+
+extern "C" int gnb_default_config(gnb_config* cfg) {
+    if (!cfg) return GNB_E_INVALID;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->max_keypoints = 1024;
+    cfg->nms_radius = 4;
+    cfg->keypoint_threshold = 0.005f;
+    cfg->border = 4;
+    cfg->match_threshold = 0.5f;
+    cfg->min_matches = 15;
+    cfg->ransac_iters = 2048;
+    cfg->reproj_px = 8.0f;
+    cfg->ransac_seed = 0;
+    cfg->refine = 1;
+    cfg->max_batch = 8;
+    cfg->max_image_h = 1088;
+    cfg->max_image_w = 1280;
+    cfg->conv_impl = 0;
+    cfg->match_impl = 0;
+    return GNB_OK;
+}
+
+extern "C" const char* gnb_last_error(const gnb_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" int64_t gnb_launch_count(const gnb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* gnb_stream(const gnb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int gnb_get_config(const gnb_ctx* ctx, gnb_config* out) {
+    if (!ctx || !out) return GNB_E_INVALID;
+    *out = ctx->cfg;
+    return GNB_OK;
+}
+
+int gnb_ensure_stage(gnb_ctx* ctx, size_t fa, size_t fb) {
+    if (fa > ctx->stage_a_floats) {
+        if (ctx->stage_a) cudaFree(ctx->stage_a);
+        ctx->stage_a = nullptr; ctx->stage_a_floats = 0;
+        GNB_CUDA(ctx, cudaMalloc(&ctx->stage_a, fa * sizeof(float)));
+        ctx->stage_a_floats = fa;
+    }
+    if (fb > ctx->stage_b_floats) {
+        if (ctx->stage_b) cudaFree(ctx->stage_b);
+        ctx->stage_b = nullptr; ctx->stage_b_floats = 0;
+        GNB_CUDA(ctx, cudaMalloc(&ctx->stage_b, fb * sizeof(float)));
+        ctx->stage_b_floats = fb;
+    }
+    return GNB_OK;
+}
+
+template <typename T>
+static int dalloc(gnb_ctx* ctx, T** p, size_t count) {
+    GNB_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    return GNB_OK;
+}
+
+static int alloc_workspace(gnb_ctx* ctx) {
+    const gnb_config& c = ctx->cfg;
+    ConvWorkspace& cw = ctx->cw;
+    const size_t n = c.max_batch, px = (size_t)c.max_image_h * c.max_image_w;
+    cw.cap_images = c.max_batch;
+    cw.cap_pixels = px;
+    int rc = 0;
+    rc |= dalloc(ctx, &cw.img, n * px);
+    rc |= dalloc(ctx, &cw.a1a, n * px * 64);
+    rc |= dalloc(ctx, &cw.p1, n * px / 4 * 64);
+    rc |= dalloc(ctx, &cw.a2a, n * px / 4 * 64);
+    rc |= dalloc(ctx, &cw.p2, n * px / 16 * 64);
+    rc |= dalloc(ctx, &cw.a3a, n * px / 16 * 128);
+    rc |= dalloc(ctx, &cw.p3, n * px / 64 * 128);
+    rc |= dalloc(ctx, &cw.a4a, n * px / 64 * 128);
+    rc |= dalloc(ctx, &cw.a4b, n * px / 64 * 128);
+    rc |= dalloc(ctx, &cw.apa, n * px / 64 * 256);
+    rc |= dalloc(ctx, &cw.ada, n * px / 64 * 256);
+    rc |= dalloc(ctx, &cw.semi, n * px / 64 * 65);
+    rc |= dalloc(ctx, &cw.score, n * px);
+    rc |= dalloc(ctx, &cw.dense, n * px / 64 * 256);
+    if (rc) return GNB_E_CUDA;
+    const size_t slots = 2 * n, k = c.max_keypoints, it = c.ransac_iters;
+    ctx->kp_slots = (int)slots;
+    rc |= dalloc(ctx, &ctx->cand_keys, slots * GNB_CAND_CAP);
+    rc |= dalloc(ctx, &ctx->cand_count, slots);
+    rc |= dalloc(ctx, &ctx->kp_xy, slots * k * 2);
+    rc |= dalloc(ctx, &ctx->kp_score, slots * k);
+    rc |= dalloc(ctx, &ctx->kp_count, slots);
+    rc |= dalloc(ctx, &ctx->desc_f32, slots * k * 256);
+    rc |= dalloc(ctx, &ctx->mproj, slots * k * 256);
+    rc |= dalloc(ctx, &ctx->mlogit, slots * k);
+    rc |= dalloc(ctx, &ctx->row_lse, slots * k);
+    rc |= dalloc(ctx, &ctx->best_val, slots * k);
+    rc |= dalloc(ctx, &ctx->best_idx, slots * k);
+    rc |= dalloc(ctx, &ctx->match_idx, n * k * 2);
+    rc |= dalloc(ctx, &ctx->match_score, n * k);
+    rc |= dalloc(ctx, &ctx->match_count, n);
+    rc |= dalloc(ctx, &ctx->mkp_qry, n * k * 2);
+    rc |= dalloc(ctx, &ctx->mkp_ref, n * k * 2);
+    rc |= dalloc(ctx, &ctx->obj, n * k * 3);
+    rc |= dalloc(ctx, &ctx->hyp, n * it * 12);
+    rc |= dalloc(ctx, &ctx->hyp_count, n * it);
+    rc |= dalloc(ctx, &ctx->inlier_mask, n * k);
+    rc |= dalloc(ctx, &ctx->range_flag, n);
+    rc |= dalloc(ctx, &ctx->kmat, n * 9);
+    rc |= dalloc(ctx, &ctx->affine, n * 12);
+    rc |= dalloc(ctx, &ctx->dem, n * px);
+    rc |= dalloc(ctx, &ctx->out_dev, n);
+    if (rc) return GNB_E_CUDA;
+    GNB_CUDA(ctx, cudaMemset(ctx->kp_count, 0, slots * sizeof(int)));
+    GNB_CUDA(ctx, cudaMemset(ctx->mproj, 0, slots * k * 256 * sizeof(bf16)));
+    GNB_CUDA(ctx, cudaMemset(ctx->kp_xy, 0, slots * k * 2 * sizeof(float)));
+    GNB_CUDA(ctx, cudaMallocHost((void**)&ctx->out_host, n * sizeof(PairOut)));
+    return gnb_ensure_stage(ctx, 1 << 16, 1 << 16);
+}
+
+extern "C" void gnb_destroy(gnb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    gnb_conv_free(ctx);
+    gnb_match_free(ctx);
+    ConvWorkspace& cw = ctx->cw;
+    void* ptrs[] = {cw.img, cw.a1a, cw.p1, cw.a2a, cw.p2, cw.a3a, cw.p3, cw.a4a, cw.a4b, cw.apa, cw.ada, cw.semi,
+                    cw.score, cw.dense, ctx->cand_keys, ctx->cand_count, ctx->kp_xy, ctx->kp_score, ctx->kp_count,
+                    ctx->desc_f32, ctx->mproj, ctx->mlogit, ctx->row_lse, ctx->best_val, ctx->best_idx, ctx->match_idx,
+                    ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
+                    ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
+                    ctx->stage_b};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->out_host) cudaFreeHost(ctx->out_host);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int gnb_create(const gnb_config* cfg, const void* weights, size_t nbytes, int weights_on_device, int device,
+                          gnb_ctx** out) {
+    if (!cfg || !weights || !out) { snprintf(g_create_err, sizeof(g_create_err), "null argument"); return GNB_E_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        snprintf(g_create_err, sizeof(g_create_err), "no CUDA device %d (found %d); this library has no CPU fallback", device, ndev);
+        return GNB_E_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        snprintf(g_create_err, sizeof(g_create_err), "device %d is sm_%d%d; libgisnav_b200 is built for sm_100a only", device,
+                 prop.major, prop.minor);
+        return GNB_E_NO_DEVICE;
+    }
+    if (cfg->max_keypoints < 16 || cfg->max_keypoints > GNB_MAX_KP || cfg->max_batch < 1 || cfg->ransac_iters < 1 ||
+        cfg->max_image_h % 8 || cfg->max_image_w % 8 || cfg->max_image_h < 16 || cfg->max_image_w < 16) {
+        snprintf(g_create_err, sizeof(g_create_err), "invalid config (K in [16,%d], sides multiple of 8)", GNB_MAX_KP);
+        return GNB_E_INVALID;
+    }
+    gnb_ctx* ctx = new (std::nothrow) gnb_ctx();
+    if (!ctx) return GNB_E_INVALID;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->cfg = *cfg;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->err[0] = 0;
+    int rc = GNB_OK;
+    auto fail = [&](int code) {
+        snprintf(g_create_err, sizeof(g_create_err), "%s", ctx->err);
+        gnb_destroy(ctx);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) { GNB_SET_ERR(ctx, "cudaSetDevice failed"); return fail(GNB_E_CUDA); }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        GNB_SET_ERR(ctx, "stream create failed");
+        return fail(GNB_E_CUDA);
+    }
+    // weight blob: 16-byte header + floats (gisnav_b200/weights.py)
+    std::vector<uint8_t> blob(nbytes);
+    if (weights_on_device) {
+        if (cudaMemcpy(blob.data(), weights, nbytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            GNB_SET_ERR(ctx, "cannot read weights from device");
+            return fail(GNB_E_CUDA);
+        }
+    } else {
+        memcpy(blob.data(), weights, nbytes);
+    }
+    uint32_t hdr[4];
+    if (nbytes < 16) { GNB_SET_ERR(ctx, "weight blob too small"); return fail(GNB_E_INVALID); }
+    memcpy(hdr, blob.data(), 16);
+    const size_t expect_floats = 1366914;
+    if (memcmp(blob.data(), "GNBW", 4) != 0 || hdr[1] != 1 || hdr[2] != expect_floats || nbytes != 16 + 4 * expect_floats) {
+        GNB_SET_ERR(ctx, "bad weight blob (magic/version/size)");
+        return fail(GNB_E_INVALID);
+    }
+    const float* fl = reinterpret_cast<const float*>(blob.data() + 16);
+    if ((rc = gnb_conv_init(ctx, fl))) return fail(rc);
+    const float* head = fl + (expect_floats - (256 * 256 + 256 + 256 + 1));
+    if ((rc = gnb_match_init(ctx, head, head + 256 * 256, head + 256 * 256 + 256, head[256 * 256 + 512]))) return fail(rc);
+    if ((rc = alloc_workspace(ctx))) return fail(rc);
+    if (cfg->conv_impl == 0 && (rc = gnb_conv_tc_init(ctx))) return fail(rc);
+    if (cfg->match_impl == 0 && (rc = gnb_match_tc_init(ctx))) return fail(rc);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { GNB_SET_ERR(ctx, "init sync failed"); return fail(GNB_E_CUDA); }
+    *out = ctx;
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static cudaMemcpyKind kind_in(int on_device) { return on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+static cudaMemcpyKind kind_out(int on_device) { return on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
+static int check_image(gnb_ctx* ctx, int h, int w) {
+    if (h <= 0 || w <= 0 || (h % 8) || (w % 8)) {
+        GNB_SET_ERR(ctx, "image sides must be positive multiples of 8 (got %dx%d)", h, w);
+        return GNB_E_INVALID;
+    }
+    if ((size_t)h * w > ctx->cw.cap_pixels) {
+        GNB_SET_ERR(ctx, "image %dx%d exceeds the workspace (%d x %d)", h, w, ctx->cfg.max_image_h, ctx->cfg.max_image_w);
+        return GNB_E_CAPACITY;
+    }
+    return GNB_OK;
+}
+
+static int read_count(gnb_ctx* ctx, const int* dptr, int* out) {
+    GNB_CUDA(ctx, cudaMemcpyAsync(out, dptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GNB_OK;
+}
+
+extern "C" int gnb_extract(gnb_ctx* ctx, const uint8_t* image, int h, int w, int stride, int on_device, float* out_xy,
+                           float* out_score, float* out_desc, int cap, int* n_out) {
+    if (!ctx || !image || !n_out) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_image(ctx, h, w))) return rc;
+    if (stride < w) { GNB_SET_ERR(ctx, "stride < width"); return GNB_E_INVALID; }
+    GNB_CUDA(ctx, cudaMemcpy2DAsync(ctx->cw.img, w, image, stride, w, h, kind_in(on_device), ctx->stream));
+    if ((rc = gnb_conv_forward(ctx, 1, h, w))) return rc;
+    if ((rc = gnb_kp_select(ctx, ctx->cw.score, 1, h, w, 0))) return rc;
+    if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, 1, h, w, 0))) return rc;
+    int n = 0;
+    if ((rc = read_count(ctx, ctx->kp_count, &n))) return rc;
+    if (n < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); return GNB_E_CAPACITY; }
+    n = n < cap ? n : cap;
+    *n_out = n;
+    if (n > 0) {
+        if (out_xy) GNB_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->kp_xy, sizeof(float) * 2 * n, kind_out(on_device), ctx->stream));
+        if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->kp_score, sizeof(float) * n, kind_out(on_device), ctx->stream));
+        if (out_desc) GNB_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->desc_f32, sizeof(float) * 256 * n, kind_out(on_device), ctx->stream));
+        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GNB_OK;
+}
+
+__global__ void widen_idx_kernel(const int* __restrict__ in, long long* __restrict__ out, int n2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) out[i] = (long long)in[i];
+}
+
+static int load_descs(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device) {
+    const int k = ctx->cfg.max_keypoints, sb = ctx->cfg.max_batch;
+    if (n_a < 0 || n_b < 0 || n_a > k || n_b > k) {
+        GNB_SET_ERR(ctx, "descriptor count exceeds max_keypoints=%d", k);
+        return GNB_E_CAPACITY;
+    }
+    if (n_a) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->desc_f32, desc_a, sizeof(float) * 256 * n_a, kind_in(on_device), ctx->stream));
+    if (n_b) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->desc_f32 + (size_t)sb * k * 256, desc_b, sizeof(float) * 256 * n_b, kind_in(on_device), ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n_a, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count + sb, &n_b, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // n_a/n_b live on the caller's stack
+    int rc;
+    if ((rc = gnb_match_project(ctx, 0, 1))) return rc;
+    if ((rc = gnb_match_project(ctx, sb, 1))) return rc;
+    return GNB_OK;
+}
+
+extern "C" int gnb_match(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device,
+                         int64_t* out_idx, float* out_score, int cap, int* n_out) {
+    if (!ctx || !n_out) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    *n_out = 0;
+    if (n_a == 0 || n_b == 0) return GNB_OK;
+    if (!desc_a || !desc_b) return GNB_E_INVALID;
+    int rc;
+    if ((rc = load_descs(ctx, desc_a, n_a, desc_b, n_b, on_device))) return rc;
+    if ((rc = gnb_match_pairs(ctx, 1, 0, ctx->cfg.max_batch))) return rc;
+    int n = 0;
+    if ((rc = read_count(ctx, ctx->match_count, &n))) return rc;
+    n = n < cap ? n : cap;
+    *n_out = n;
+    if (n > 0) {
+        if (out_idx) {
+            if (on_device) {
+                widen_idx_kernel<<<ceil_div(2 * n, 256), 256, 0, ctx->stream>>>(ctx->match_idx, (long long*)out_idx, 2 * n);
+                GNB_LAUNCH_CHECK(ctx);
+            } else {
+                std::vector<int> tmp(2 * n);
+                GNB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->match_idx, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+                GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                for (int i = 0; i < 2 * n; ++i) out_idx[i] = tmp[i];
+            }
+        }
+        if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->match_score, sizeof(float) * n, kind_out(on_device), ctx->stream));
+        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GNB_OK;
+}
+
+static void pairout_to_result(const PairOut& p, gnb_pose_result* r) {
+    r->status = p.status; r->n_kp_qry = p.n_kp_qry; r->n_kp_ref = p.n_kp_ref; r->n_matches = p.n_matches;
+    r->n_inliers = p.n_inliers; r->best_hypothesis = p.best_hypothesis;
+    memcpy(r->r, p.r, sizeof(p.r)); memcpy(r->t, p.t, sizeof(p.t)); memcpy(r->ecef, p.ecef, sizeof(p.ecef));
+    memcpy(r->quat, p.quat, sizeof(p.quat)); memcpy(r->lla, p.lla, sizeof(p.lla));
+}
+
+extern "C" int gnb_solve_pnp(gnb_ctx* ctx, const float* mkp_qry, const float* mkp_ref, int n, const uint8_t* dem,
+                             int dem_h, int dem_w, const double* k9, int on_device, double* out_r9, double* out_t3,
+                             uint8_t* out_inlier_mask, int* n_inliers) {
+    if (!ctx || !k9 || n < 0 || (n > 0 && (!mkp_qry || !mkp_ref))) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n > ctx->cfg.max_keypoints) { GNB_SET_ERR(ctx, "n=%d exceeds max_keypoints", n); return GNB_E_CAPACITY; }
+    if (dem && (size_t)dem_h * dem_w > ctx->cw.cap_pixels) { GNB_SET_ERR(ctx, "DEM exceeds the workspace"); return GNB_E_CAPACITY; }
+    if (n_inliers) *n_inliers = 0;
+    if (n < 4) return GNB_SOFT_PNP_FAILED;  // cv2.solvePnPRansac returns False below the minimal set
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->mkp_qry, mkp_qry, sizeof(float) * 2 * n, kind_in(on_device), ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->mkp_ref, mkp_ref, sizeof(float) * 2 * n, kind_in(on_device), ctx->stream));
+    if (dem) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dem, (size_t)dem_h * dem_w, kind_in(on_device), ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kmat, k9, sizeof(double) * 9, kind_in(on_device), ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->match_count, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc;
+    if ((rc = gnb_pnp_pairs(ctx, 1, dem_h, dem_w, dem ? 1 : 0, 0, 0, 0, 4, 0))) return rc;
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut), cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const PairOut& p = ctx->out_host[0];
+    if (p.status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM raster"); return GNB_E_RANGE; }
+    if (n_inliers) *n_inliers = p.n_inliers;
+    if (out_r9) memcpy(out_r9, p.r, sizeof(p.r));
+    if (out_t3) memcpy(out_t3, p.t, sizeof(p.t));
+    if (out_inlier_mask) {
+        GNB_CUDA(ctx, cudaMemcpyAsync(out_inlier_mask, ctx->inlier_mask, n, kind_out(on_device), ctx->stream));
+        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return p.status;
+}
+
+extern "C" int gnb_geodetic_tail(gnb_ctx* ctx, const double* r9, const double* t3, const double* affine12, int ref_h,
+                                 int ref_w, double* out_ecef3, double* out_quat4, double* out_lla3) {
+    if (!ctx || !r9 || !t3 || !affine12 || !out_ecef3 || !out_quat4 || !out_lla3) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return gnb_tail_device(ctx, r9, t3, affine12, ref_h, ref_w, out_ecef3, out_quat4, out_lla3);
+}
+
+extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, int hq, int wq, const uint8_t* tiles, int ht,
+                              int wt, const uint8_t* dems, const double* k9, const double* affine12, int on_device,
+                              gnb_pose_result* results) {
+    if (!ctx || !frames || !tiles || !k9 || !affine12 || !results || batch < 1) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (batch > ctx->cfg.max_batch) { GNB_SET_ERR(ctx, "batch %d exceeds max_batch %d", batch, ctx->cfg.max_batch); return GNB_E_CAPACITY; }
+    int rc;
+    if ((rc = check_image(ctx, hq, wq)) || (rc = check_image(ctx, ht, wt))) return rc;
+    const int sb = ctx->cfg.max_batch;
+    const cudaMemcpyKind kin = kind_in(on_device);
+    // small per-pair parameters first so they overlap with the first conv pass
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kmat, k9, sizeof(double) * 9 * batch, kin, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->affine, affine12, sizeof(double) * 12 * batch, kin, ctx->stream));
+    if (dems) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dems, (size_t)batch * ht * wt, kin, ctx->stream));
+    // query frames -> slots [0, batch)
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.img, frames, (size_t)batch * hq * wq, kin, ctx->stream));
+    if ((rc = gnb_conv_forward(ctx, batch, hq, wq))) return rc;
+    if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, hq, wq, 0))) return rc;
+    if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, batch, hq, wq, 0))) return rc;
+    // reference rasters -> slots [max_batch, max_batch + batch)
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.img, tiles, (size_t)batch * ht * wt, kin, ctx->stream));
+    if ((rc = gnb_conv_forward(ctx, batch, ht, wt))) return rc;
+    if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, ht, wt, sb))) return rc;
+    if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, batch, ht, wt, sb))) return rc;
+    if ((rc = gnb_match_project(ctx, 0, batch))) return rc;
+    if ((rc = gnb_match_project(ctx, sb, batch))) return rc;
+    if ((rc = gnb_match_pairs(ctx, batch, 0, sb))) return rc;
+    if ((rc = gnb_pnp_pairs(ctx, batch, ht, wt, dems ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1))) return rc;
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < batch; ++b) {
+        pairout_to_result(ctx->out_host[b], &results[b]);
+        if (results[b].n_kp_qry < 0 || results[b].n_kp_ref < 0) {
+            GNB_SET_ERR(ctx, "NMS candidate buffer overflow in pair %d", b);
+            return GNB_E_CAPACITY;
+        }
+        if (results[b].status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM in pair %d", b); return GNB_E_RANGE; }
+    }
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-isolated hooks
+extern "C" int gnb_dense(gnb_ctx* ctx, const uint8_t* image, int h, int w, int stride, float* out_score, float* out_dense) {
+    if (!ctx || !image) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_image(ctx, h, w))) return rc;
+    GNB_CUDA(ctx, cudaMemcpy2DAsync(ctx->cw.img, w, image, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = gnb_conv_forward(ctx, 1, h, w))) return rc;
+    if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->cw.score, sizeof(float) * h * w, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_dense) GNB_CUDA(ctx, cudaMemcpyAsync(out_dense, ctx->cw.dense, sizeof(float) * (h / 8) * (w / 8) * 256, cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GNB_OK;
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out, size_t out_floats) {
+    if (!ctx || !layer || !out) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ConvWorkspace& cw = ctx->cw;
+    struct { const char* name; const bf16* p; int div, c; } tbl[] = {
+        {"conv1a", cw.a1a, 1, 64}, {"pool1", cw.p1, 2, 64},   {"conv2a", cw.a2a, 2, 64}, {"pool2", cw.p2, 4, 64},
+        {"conv3a", cw.a3a, 4, 128}, {"pool3", cw.p3, 8, 128}, {"conv4a", cw.a4a, 8, 128}, {"conv4b", cw.a4b, 8, 128},
+        {"convPa", cw.apa, 8, 256}, {"convDa", cw.ada, 8, 256},
+    };
+    for (auto& t : tbl) {
+        if (strcmp(t.name, layer) == 0) {
+            const size_t n = (size_t)(cw.h / t.div) * (cw.w / t.div) * t.c;
+            if (n != out_floats) { GNB_SET_ERR(ctx, "layer %s has %zu floats, caller passed %zu", layer, n, out_floats); return GNB_E_INVALID; }
+            int rc;
+            if ((rc = gnb_ensure_stage(ctx, n, 0))) return rc;
+            bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t.p, ctx->stage_a, n);
+            GNB_LAUNCH_CHECK(ctx);
+            GNB_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage_a, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return GNB_OK;
+        }
+    }
+    if (strcmp(layer, "semi") == 0) {
+        const size_t n = (size_t)(cw.h / 8) * (cw.w / 8) * 65;
+        if (n != out_floats) return GNB_E_INVALID;
+        GNB_CUDA(ctx, cudaMemcpyAsync(out, cw.semi, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return GNB_OK;
+    }
+    GNB_SET_ERR(ctx, "unknown layer '%s'", layer);
+    return GNB_E_INVALID;
+}
+
+extern "C" int gnb_select_keypoints(gnb_ctx* ctx, const float* score, int h, int w, float* out_xy, float* out_score,
+                                    int cap, int* n_out) {
+    if (!ctx || !score || !n_out) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (h <= 0 || w <= 0 || (size_t)h * w > ctx->cw.cap_pixels) { GNB_SET_ERR(ctx, "score map exceeds the workspace"); return GNB_E_CAPACITY; }
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.score, score, sizeof(float) * h * w, cudaMemcpyHostToDevice, ctx->stream));
+    int rc;
+    if ((rc = gnb_kp_select(ctx, ctx->cw.score, 1, h, w, 0))) return rc;
+    int n = 0;
+    if ((rc = read_count(ctx, ctx->kp_count, &n))) return rc;
+    if (n < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); return GNB_E_CAPACITY; }
+    n = n < cap ? n : cap;
+    *n_out = n;
+    if (n > 0) {
+        if (out_xy) GNB_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->kp_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->kp_score, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GNB_OK;
+}
+
+extern "C" int gnb_sample_descriptors(gnb_ctx* ctx, const float* dense, int hc, int wc, const float* xy, int n, int img_h,
+                                      int img_w, float* out_desc) {
+    if (!ctx || !dense || (n > 0 && (!xy || !out_desc))) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n > ctx->cfg.max_keypoints || (size_t)hc * wc * 64 > ctx->cw.cap_pixels) { GNB_SET_ERR(ctx, "exceeds workspace"); return GNB_E_CAPACITY; }
+    if (n == 0) return GNB_OK;
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.dense, dense, sizeof(float) * hc * wc * 256, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_xy, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // the sampler derives hc,wc from the image size; honour the caller's explicit map size
+    if (hc != img_h / 8 || wc != img_w / 8) { GNB_SET_ERR(ctx, "dense map must be image/8"); return GNB_E_INVALID; }
+    int rc;
+    if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, 1, img_h, img_w, 0))) return rc;
+    GNB_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->desc_f32, sizeof(float) * 256 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GNB_OK;
+}
+
+// full score matrix for small problems: one thread per (i, j), direct dot product of the
+// projected descriptors + the LSE vectors of pass 0.
+__global__ void score_matrix_kernel(const bf16* __restrict__ ma, const bf16* __restrict__ mb, const float* __restrict__ lse_a,
+                                    const float* __restrict__ lse_b, const float* __restrict__ la,
+                                    const float* __restrict__ lb, int na, int nb, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= nb || i >= na) return;
+    float s = 0.f;
+    for (int k = 0; k < 256; ++k) s = fmaf(__bfloat162float(ma[(size_t)i * 256 + k]), __bfloat162float(mb[(size_t)j * 256 + k]), s);
+    out[(size_t)i * nb + j] = __fadd_rn(__fadd_rn(__fadd_rn(__fsub_rn(s, lse_a[i]), __fsub_rn(s, lse_b[j])), la[i]), lb[j]);
+}
+
+extern "C" int gnb_match_scores(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, float* out_scores) {
+    if (!ctx || !desc_a || !desc_b || !out_scores || n_a < 1 || n_b < 1) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = load_descs(ctx, desc_a, n_a, desc_b, n_b, 0))) return rc;
+    if ((rc = gnb_match_pairs(ctx, 1, 0, ctx->cfg.max_batch))) return rc;  // fills row_lse for both sides
+    if ((rc = gnb_ensure_stage(ctx, (size_t)n_a * n_b, 0))) return rc;
+    const int k = ctx->cfg.max_keypoints, sb = ctx->cfg.max_batch;
+    dim3 grid(ceil_div(n_b, 128), n_a);
+    score_matrix_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->mproj, ctx->mproj + (size_t)sb * k * 256, ctx->row_lse,
+                                                       ctx->row_lse + (size_t)sb * k, ctx->mlogit, ctx->mlogit + (size_t)sb * k,
+                                                       n_a, n_b, ctx->stage_a);
+    GNB_LAUNCH_CHECK(ctx);
+    GNB_CUDA(ctx, cudaMemcpyAsync(out_scores, ctx->stage_a, sizeof(float) * n_a * n_b, cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GNB_OK;
+}
+
+extern "C" int gnb_ransac_debug(gnb_ctx* ctx, int32_t* out_counts, float* out_hyp, int* out_best) {
+    if (!ctx) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int it = ctx->cfg.ransac_iters;
+    if (out_counts) GNB_CUDA(ctx, cudaMemcpyAsync(out_counts, ctx->hyp_count, sizeof(int) * it, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_hyp) GNB_CUDA(ctx, cudaMemcpyAsync(out_hyp, ctx->hyp, sizeof(float) * 12 * it, cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_best) *out_best = ctx->out_host[0].best_hypothesis;
+    return GNB_OK;
+}

@@ -1,0 +1,145 @@
+// common.cuh — context, workspace and launch helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gisnav_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+#define GNB_NUM_LAYERS 12
+#define GNB_CAND_CAP 65536  // NMS survivors kept per image before top-K
+#define GNB_MAX_KP 4096     // hard ceiling for cfg.max_keypoints
+
+enum LayerId { L1A = 0, L1B, L2A, L2B, L3A, L3B, L4A, L4B, LPA, LPB, LDA, LDB };
+
+struct ConvLayer {
+    int cin, cout, ks, cout_pad;
+    bf16* w;      // device, [ks*ks][cout_pad][cin]  (K-major per tap: tcgen05 B operand / SIMT)
+    float* bias;  // device, [cout_pad]
+};
+
+// Per-image-slot activation pointers for one batched pass of the conv stack (all NHWC).
+struct ConvWorkspace {
+    int cap_images;       // images per pass
+    size_t cap_pixels;    // max h*w per image
+    uint8_t* img;         // [n][h][w]
+    bf16 *a1a, *p1, *a2a, *p2, *a3a, *p3, *a4a, *a4b, *apa, *ada;
+    float* semi;          // [n][hc][wc][65]
+    float* score;         // [n][h][w]
+    float* dense;         // [n][hc][wc][256]  L2-normalised
+    int n, h, w;          // shape of the last pass (for gnb_layer_activation)
+};
+
+// Device-side mirror of gnb_pose_result with the fields the kernels fill.
+struct PairOut {
+    int32_t status, n_kp_qry, n_kp_ref, n_matches, n_inliers, best_hypothesis, pad0, pad1;
+    double r[9], t[3], ecef[3], quat[4], lla[3];
+};
+
+struct gnb_ctx {
+    gnb_config cfg;
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    char err[512];
+    int64_t launches;
+    ConvLayer layers[GNB_NUM_LAYERS];
+    // matcher head
+    bf16* match_w;    // [256 out][256 in]
+    float* match_b;   // [256]
+    bf16* match_mw;   // [256]
+    float match_mb;
+    ConvWorkspace cw;
+    // keypoints: slots 0..2*max_batch-1 (frames then tiles)
+    int kp_slots;
+    unsigned long long* cand_keys;  // [slots][GNB_CAND_CAP]
+    int* cand_count;                // [slots]
+    float* kp_xy;                   // [slots][K][2]
+    float* kp_score;                // [slots][K]
+    int* kp_count;                  // [slots]
+    float* desc_f32;                // [slots][K][256]
+    // matcher, per pair
+    bf16* mproj;                    // [slots][K][256]
+    float* mlogit;                  // [slots][K]   logsigmoid(z)
+    float* row_lse;                 // [slots][K]   LSE over the other side
+    float* best_val;                // [slots][K]
+    int* best_idx;                  // [slots][K]
+    int* match_idx;                 // [pairs][K][2]
+    float* match_score;             // [pairs][K]
+    int* match_count;               // [pairs]
+    float* mkp_qry;                 // [pairs][K][2]
+    float* mkp_ref;                 // [pairs][K][2]
+    // PnP, per pair
+    float* obj;                     // [pairs][K][3]
+    float* hyp;                     // [pairs][iters][12]
+    int* hyp_count;                 // [pairs][iters]
+    uint8_t* inlier_mask;           // [pairs][K]
+    int* range_flag;                // [pairs]
+    double* kmat;                   // [pairs][9]
+    double* affine;                 // [pairs][12]
+    uint8_t* dem;                   // [pairs][h][w]
+    PairOut* out_dev;               // [pairs]
+    PairOut* out_host;              // pinned [pairs]
+    // staging for the stage-level entry points
+    float* stage_a;                 // generic device scratch (floats)
+    size_t stage_a_floats;
+    float* stage_b;
+    size_t stage_b_floats;
+};
+
+#define GNB_SET_ERR(ctx, ...)                                   \
+    do {                                                        \
+        if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    } while (0)
+
+#define GNB_CUDA(ctx, expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            GNB_SET_ERR(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return GNB_E_CUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define GNB_LAUNCH_CHECK(ctx)                          \
+    do {                                               \
+        (ctx)->launches++;                             \
+        GNB_CUDA(ctx, cudaGetLastError());             \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- stage functions implemented across the .cu files (all enqueue on ctx->stream) -----------
+int gnb_conv_init(gnb_ctx* ctx, const float* blob_floats);  // repack weights
+void gnb_conv_free(gnb_ctx* ctx);
+// run the dense stack on cw.img (n images of h x w already resident)
+int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w);
+// tcgen05 implicit-GEMM conv (conv_tc.cu); returns GNB_E_INVALID if a layer shape is unsupported
+int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, int h, int w, bf16* out_bf,
+                      float* out_f, int relu, int pool);
+int gnb_conv_tc_init(gnb_ctx* ctx);
+
+// keypoints.cu
+int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slot0);
+int gnb_kp_sample(gnb_ctx* ctx, const float* dense, int n, int h, int w, int slot0);
+
+// match.cu
+int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const float* m_w, float m_b);
+void gnb_match_free(gnb_ctx* ctx);
+// project descriptors of `n_slots` consecutive slots
+int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots);
+// match slot_a[p] against slot_b[p] for p in [0, pairs): fills match_idx/score/count + mkp_*
+int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0);
+int gnb_match_tc_init(gnb_ctx* ctx);
+int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int pass);
+
+// pnp.cu
+int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, int ref_h, int ref_w, int do_tail,
+                  int min_matches, int use_kp_counts);
+int gnb_tail_device(gnb_ctx* ctx, const double* r9, const double* t3, const double* affine12, int ref_h, int ref_w,
+                    double* ecef3, double* quat4, double* lla3);
+int gnb_ensure_stage(gnb_ctx* ctx, size_t floats_a, size_t floats_b);

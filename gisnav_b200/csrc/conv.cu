@@ -1,0 +1,297 @@
+// conv.cu — K1: the SuperPoint-style dense stack (replaces cv2.SIFT.detectAndCompute,
+// ros/gisnav/gisnav/core/pose_node.py:230; architecture per SURVEY.md §8(c)).
+//
+// Numerics contract (oracle/superpoint_ref.py): conv operands (activations, weights) are bf16,
+// accumulation fp32, bias fp32, ReLU, activations stored back as bf16 NHWC.  Heads stay fp32.
+//
+// This file holds weight repacking, the Cin=1 first layer, the detector/descriptor head epilogues
+// and a SIMT validation implementation of the 3x3/1x1 convs (cfg.conv_impl = 1).  The product
+// path for the Cin>=64 layers is the tcgen05 implicit GEMM in conv_tc.cu.
+#include "common.cuh"
+
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// host-side bf16 rounding (round to nearest even), identical to torch's .to(bfloat16)
+static inline uint16_t f32_to_bf16_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    uint32_t lsb = (u >> 16) & 1u;
+    u += 0x7fffu + lsb;
+    return (uint16_t)(u >> 16);
+}
+
+struct LayerSpec { const char* name; int cin, cout, ks; };
+static const LayerSpec kSpecs[GNB_NUM_LAYERS] = {
+    {"conv1a", 1, 64, 3},   {"conv1b", 64, 64, 3},   {"conv2a", 64, 64, 3},   {"conv2b", 64, 64, 3},
+    {"conv3a", 64, 128, 3}, {"conv3b", 128, 128, 3}, {"conv4a", 128, 128, 3}, {"conv4b", 128, 128, 3},
+    {"convPa", 128, 256, 3}, {"convPb", 256, 65, 1}, {"convDa", 128, 256, 3}, {"convDb", 256, 256, 1},
+};
+
+int gnb_conv_init(gnb_ctx* ctx, const float* blob) {
+    size_t off = 0;
+    for (int l = 0; l < GNB_NUM_LAYERS; ++l) {
+        const LayerSpec& s = kSpecs[l];
+        ConvLayer& L = ctx->layers[l];
+        L.cin = s.cin; L.cout = s.cout; L.ks = s.ks;
+        L.cout_pad = (s.cout + 15) / 16 * 16;
+        const int taps = s.ks * s.ks;
+        const float* w = blob + off;                       // [cout][cin][ks][ks]
+        const float* b = w + (size_t)s.cout * s.cin * taps;  // [cout]
+        off += (size_t)s.cout * s.cin * taps + s.cout;
+        std::vector<uint16_t> wp((size_t)taps * L.cout_pad * s.cin, 0);
+        std::vector<float> bp(L.cout_pad, 0.f);
+        for (int co = 0; co < s.cout; ++co) {
+            bp[co] = b[co];
+            for (int ci = 0; ci < s.cin; ++ci)
+                for (int t = 0; t < taps; ++t)
+                    wp[((size_t)t * L.cout_pad + co) * s.cin + ci] = f32_to_bf16_bits(w[((size_t)co * s.cin + ci) * taps + t]);
+        }
+        GNB_CUDA(ctx, cudaMalloc(&L.w, wp.size() * sizeof(uint16_t)));
+        GNB_CUDA(ctx, cudaMalloc(&L.bias, bp.size() * sizeof(float)));
+        GNB_CUDA(ctx, cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        GNB_CUDA(ctx, cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return GNB_OK;
+}
+
+void gnb_conv_free(gnb_ctx* ctx) {
+    for (int l = 0; l < GNB_NUM_LAYERS; ++l) {
+        if (ctx->layers[l].w) cudaFree(ctx->layers[l].w);
+        if (ctx->layers[l].bias) cudaFree(ctx->layers[l].bias);
+        ctx->layers[l].w = nullptr; ctx->layers[l].bias = nullptr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1a: u8 image -> 64 channels, 3x3, ReLU, bf16 NHWC.  Cin = 1, so this is 9 FMAs per output:
+// HBM-bound (1 B in, 128 B out per pixel).  One thread per pixel, 16-byte stores.
+__global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__ img, const bf16* __restrict__ wt,
+                                                     const float* __restrict__ bias, int h, int w, bf16* __restrict__ out) {
+    __shared__ float wsm[9][64];
+    __shared__ float bsm[64];
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) wsm[i / 64][i % 64] = __bfloat162float(wt[i]);
+    if (threadIdx.x < 64) bsm[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const uint8_t* im = img + (size_t)b * h * w;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        float f = 0.f;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) f = (float)im[(size_t)yy * w + xx] / 255.0f;
+        v[t] = __bfloat162float(__float2bfloat16_rn(f));
+    }
+    bf16* o = out + ((size_t)b * h * w + (size_t)y * w + x) * 64;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+        __align__(16) bf16 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wsm[t][c0 + j], acc);
+            acc += bsm[c0 + j];
+            r[j] = __float2bfloat16_rn(fmaxf(acc, 0.f));
+        }
+        *reinterpret_cast<uint4*>(o + c0) = *reinterpret_cast<const uint4*>(r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT validation conv: 8x16 pixel tile per CTA, one pixel per thread, 16 output channels at a time.
+template <int CIN, int KS>
+__global__ void __launch_bounds__(128) conv_simt_kernel(const bf16* __restrict__ in, const bf16* __restrict__ wt,
+                                                        const float* __restrict__ bias, int h, int w, int cout,
+                                                        int cout_pad, bf16* __restrict__ out_bf,
+                                                        float* __restrict__ out_f, int relu, int pool) {
+    constexpr int R = KS / 2, TH = 8, TW = 16, HW = TW + 2 * R, HH = TH + 2 * R;
+    constexpr int CP = CIN + 2;  // padded pixel pitch (bf16 elements) -> conflict-free column reads
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    bf16* tile = reinterpret_cast<bf16*>(smem_raw);
+    float* wsm = reinterpret_cast<float*>(smem_raw + ((HH * HW * CP * 2 + 15) / 16) * 16);
+    const int tid = threadIdx.x, b = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+    const bf16* inb = in + (size_t)b * h * w * CIN;
+    for (int i = tid; i < HH * HW * (CIN / 2); i += 128) {
+        int p = i / (CIN / 2), v = i % (CIN / 2);
+        int yy = y0 - R + p / HW, xx = x0 - R + p % HW;
+        uint32_t val = 0;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+            val = *reinterpret_cast<const uint32_t*>(inb + ((size_t)yy * w + xx) * CIN + v * 2);
+        *reinterpret_cast<uint32_t*>(tile + p * CP + v * 2) = val;
+    }
+    const int ty = tid / TW, tx = tid % TW;
+    const int y = y0 + ty, x = x0 + tx;
+    for (int c0 = 0; c0 < cout_pad; c0 += 16) {
+        __syncthreads();
+        for (int i = tid; i < KS * KS * 16 * CIN; i += 128) {
+            int ci = i % CIN, j = (i / CIN) % 16, t = i / (CIN * 16);
+            wsm[(t * CIN + ci) * 16 + j] = __bfloat162float(wt[((size_t)t * cout_pad + c0 + j) * CIN + ci]);
+        }
+        __syncthreads();
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int t = 0; t < KS * KS; ++t) {
+            const bf16* a = tile + ((ty + t / KS) * HW + tx + t % KS) * CP;
+            const float* wrow = wsm + (size_t)t * CIN * 16;
+#pragma unroll 4
+            for (int ci = 0; ci < CIN; ci += 2) {
+                __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(a + ci);
+                float a0 = __low2float(av), a1 = __high2float(av);
+                const float4* w0 = reinterpret_cast<const float4*>(wrow + ci * 16);
+                const float4* w1 = w0 + 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 wa = w0[q], wb = w1[q];
+                    acc[4 * q + 0] = fmaf(a0, wa.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(a0, wa.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(a0, wa.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(a0, wa.w, acc[4 * q + 3]);
+                    acc[4 * q + 0] = fmaf(a1, wb.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(a1, wb.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(a1, wb.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(a1, wb.w, acc[4 * q + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float v = acc[j] + bias[c0 + j];
+            if (relu) v = fmaxf(v, 0.f);
+            if (pool) {
+                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+            }
+            acc[j] = v;
+        }
+        if (pool) {
+            if (((tx | ty) & 1) == 0 && y < h && x < w) {
+                const int ho = h / 2, wo = w / 2;
+                bf16* o = out_bf + (((size_t)b * ho + y / 2) * wo + x / 2) * cout + c0;
+                for (int j = 0; j < 16 && c0 + j < cout; ++j) o[j] = __float2bfloat16_rn(acc[j]);
+            }
+        } else if (y < h && x < w) {
+            size_t pix = ((size_t)b * h + y) * w + x;
+            if (out_bf) {
+                bf16* o = out_bf + pix * cout + c0;
+                for (int j = 0; j < 16 && c0 + j < cout; ++j) o[j] = __float2bfloat16_rn(acc[j]);
+            } else {
+                float* o = out_f + pix * cout + c0;
+                for (int j = 0; j < 16 && c0 + j < cout; ++j) o[j] = acc[j];
+            }
+        }
+    }
+}
+
+template <int CIN, int KS>
+static int launch_conv_simt(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, int h, int w, bf16* out_bf,
+                            float* out_f, int relu, int pool) {
+    constexpr int R = KS / 2;
+    size_t smem = (((8 + 2 * R) * (16 + 2 * R) * (CIN + 2) * 2 + 15) / 16) * 16 + (size_t)KS * KS * 16 * CIN * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_simt_kernel<CIN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(w, 16), ceil_div(h, 8), n);
+    conv_simt_kernel<CIN, KS><<<grid, 128, smem, ctx->stream>>>(in, L.w, L.bias, h, w, L.cout, L.cout_pad, out_bf, out_f, relu, pool);
+    GNB_LAUNCH_CHECK(ctx);
+    return GNB_OK;
+}
+
+static int conv_layer(gnb_ctx* ctx, int lid, const bf16* in, int n, int h, int w, bf16* out_bf, float* out_f,
+                      int relu, int pool) {
+    const ConvLayer& L = ctx->layers[lid];
+    if (ctx->cfg.conv_impl == 0) {
+        int rc = gnb_conv_tc_layer(ctx, L, in, n, h, w, out_bf, out_f, relu, pool);
+        if (rc != GNB_E_INVALID) return rc;
+        GNB_SET_ERR(ctx, "tcgen05 conv does not support layer %d (cin %d cout %d ks %d)", lid, L.cin, L.cout, L.ks);
+        return rc;
+    }
+    if (L.cin == 64 && L.ks == 3) return launch_conv_simt<64, 3>(ctx, L, in, n, h, w, out_bf, out_f, relu, pool);
+    if (L.cin == 128 && L.ks == 3) return launch_conv_simt<128, 3>(ctx, L, in, n, h, w, out_bf, out_f, relu, pool);
+    if (L.cin == 256 && L.ks == 1) return launch_conv_simt<256, 1>(ctx, L, in, n, h, w, out_bf, out_f, relu, pool);
+    GNB_SET_ERR(ctx, "unsupported conv layer shape");
+    return GNB_E_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------------
+// detector head epilogue: softmax over 65 logits per cell, drop dustbin, 8x8 depth-to-space.
+// HBM-bound: 260 B in, 256 B out per cell.  One thread per cell.
+__global__ void __launch_bounds__(128) softmax_d2s_kernel(const float* __restrict__ semi, int n_cells_total, int hc,
+                                                          int wc, float* __restrict__ score) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells_total) return;
+    const float* s = semi + (size_t)cell * 65;
+    float v[65];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 65; ++i) { v[i] = s[i]; m = fmaxf(m, v[i]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 65; ++i) { v[i] = expf(v[i] - m); sum += v[i]; }
+    const float inv = 1.0f / sum;
+    const int b = cell / (hc * wc), rem = cell % (hc * wc), cy = rem / wc, cx = rem % wc;
+    const int w = wc * 8;
+    float* o = score + ((size_t)b * hc * 8 + (size_t)cy * 8) * w + (size_t)cx * 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        float4 lo = make_float4(v[r * 8 + 0] * inv, v[r * 8 + 1] * inv, v[r * 8 + 2] * inv, v[r * 8 + 3] * inv);
+        float4 hi = make_float4(v[r * 8 + 4] * inv, v[r * 8 + 5] * inv, v[r * 8 + 6] * inv, v[r * 8 + 7] * inv);
+        *reinterpret_cast<float4*>(o + (size_t)r * w) = lo;
+        *reinterpret_cast<float4*>(o + (size_t)r * w + 4) = hi;
+    }
+}
+
+// descriptor head epilogue: L2-normalise 256 channels per cell in place. One warp per cell.
+__global__ void __launch_bounds__(256) l2norm256_kernel(float* __restrict__ d, int n_cells_total) {
+    const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (cell >= n_cells_total) return;
+    float4* p = reinterpret_cast<float4*>(d + (size_t)cell * 256);
+    float4 a = p[lane], b = p[lane + 32];
+    float ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv; b.x *= inv; b.y *= inv; b.z *= inv; b.w *= inv;
+    p[lane] = a; p[lane + 32] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w) {
+    ConvWorkspace& cw = ctx->cw;
+    if (n > cw.cap_images || (size_t)h * w > cw.cap_pixels || (h % 8) || (w % 8)) {
+        GNB_SET_ERR(ctx, "conv_forward: %d images of %dx%d exceed the workspace or are not multiples of 8", n, h, w);
+        return GNB_E_CAPACITY;
+    }
+    cw.n = n; cw.h = h; cw.w = w;
+    int rc;
+    {
+        dim3 grid(ceil_div(w, 32), ceil_div(h, 8), n);
+        conv1a_kernel<<<grid, 256, 0, ctx->stream>>>(cw.img, ctx->layers[L1A].w, ctx->layers[L1A].bias, h, w, cw.a1a);
+        GNB_LAUNCH_CHECK(ctx);
+    }
+    if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
+    if ((rc = conv_layer(ctx, L2A, cw.p1, n, h / 2, w / 2, cw.a2a, nullptr, 1, 0))) return rc;
+    if ((rc = conv_layer(ctx, L2B, cw.a2a, n, h / 2, w / 2, cw.p2, nullptr, 1, 1))) return rc;
+    if ((rc = conv_layer(ctx, L3A, cw.p2, n, h / 4, w / 4, cw.a3a, nullptr, 1, 0))) return rc;
+    if ((rc = conv_layer(ctx, L3B, cw.a3a, n, h / 4, w / 4, cw.p3, nullptr, 1, 1))) return rc;
+    if ((rc = conv_layer(ctx, L4A, cw.p3, n, h / 8, w / 8, cw.a4a, nullptr, 1, 0))) return rc;
+    if ((rc = conv_layer(ctx, L4B, cw.a4a, n, h / 8, w / 8, cw.a4b, nullptr, 1, 0))) return rc;
+    if ((rc = conv_layer(ctx, LPA, cw.a4b, n, h / 8, w / 8, cw.apa, nullptr, 1, 0))) return rc;
+    if ((rc = conv_layer(ctx, LPB, cw.apa, n, h / 8, w / 8, nullptr, cw.semi, 0, 0))) return rc;
+    if ((rc = conv_layer(ctx, LDA, cw.a4b, n, h / 8, w / 8, cw.ada, nullptr, 1, 0))) return rc;
+    if ((rc = conv_layer(ctx, LDB, cw.ada, n, h / 8, w / 8, nullptr, cw.dense, 0, 0))) return rc;
+    const int cells = n * (h / 8) * (w / 8);
+    softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score);
+    GNB_LAUNCH_CHECK(ctx);
+    l2norm256_kernel<<<ceil_div(cells * 32, 256), 256, 0, ctx->stream>>>(cw.dense, cells);
+    GNB_LAUNCH_CHECK(ctx);
+    return GNB_OK;
+}

@@ -1,0 +1,278 @@
+// keypoints.cu — K2 (NMS + threshold + border + top-K) and K3 (descriptor sampling).
+//
+// K2 restates SuperPoint's simple_nms (two suppression refinements of a 9x9 max-pool), the score
+// threshold, the four-sided border removal and a top-K whose order is DEFINED as ascending
+// (-score, y*W+x) — oracle/nms_ref.py.  It is compare-only work, so the result is bit-identical
+// to the oracle on the same score map.  Replaces the detector half of cv2.SIFT.detectAndCompute
+// (ros/gisnav/gisnav/core/pose_node.py:230) and the keypoint list handling at pose_node.py:244-252.
+//
+// K3 restates SuperPoint's sample_descriptors (oracle/sample_ref.py).
+#include "common.cuh"
+
+#include <math.h>
+
+#define NMS_TILE 32
+#define NMS_HALO 20  // 5 pools x radius 4
+#define NMS_REG (NMS_TILE + 2 * NMS_HALO)
+
+// separable (2r+1)^2 max over a REG x REG smem array; window clipped to the array (== -inf pad)
+__device__ __forceinline__ void pool_rows(const float* __restrict__ src, float* __restrict__ dst, int r) {
+    for (int i = threadIdx.x; i < NMS_REG * NMS_REG; i += blockDim.x) {
+        const int y = i / NMS_REG, x = i % NMS_REG;
+        const int lo = max(x - r, 0), hi = min(x + r, NMS_REG - 1);
+        float m = src[y * NMS_REG + lo];
+        for (int xx = lo + 1; xx <= hi; ++xx) m = fmaxf(m, src[y * NMS_REG + xx]);
+        dst[i] = m;
+    }
+}
+__device__ __forceinline__ void pool_cols(const float* __restrict__ src, float* __restrict__ dst, int r) {
+    for (int i = threadIdx.x; i < NMS_REG * NMS_REG; i += blockDim.x) {
+        const int y = i / NMS_REG, x = i % NMS_REG;
+        const int lo = max(y - r, 0), hi = min(y + r, NMS_REG - 1);
+        float m = src[lo * NMS_REG + x];
+        for (int yy = lo + 1; yy <= hi; ++yy) m = fmaxf(m, src[yy * NMS_REG + x]);
+        dst[i] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ score, int h, int w, int radius,
+                                                  float threshold, int border, int slot0,
+                                                  unsigned long long* __restrict__ cand_keys,
+                                                  int* __restrict__ cand_count) {
+    extern __shared__ float sm[];
+    float* S = sm;                          // scores, -inf outside the image
+    float* T = S + NMS_REG * NMS_REG;       // row-pass temp
+    float* A = T + NMS_REG * NMS_REG;       // pooled result / suppressed scores
+    float* F = A + NMS_REG * NMS_REG;       // mask as float
+    uint8_t* M = reinterpret_cast<uint8_t*>(F + NMS_REG * NMS_REG);  // max_mask
+    uint8_t* P = M + NMS_REG * NMS_REG;                               // supp_mask
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * NMS_TILE - NMS_HALO, x0 = blockIdx.x * NMS_TILE - NMS_HALO;
+    const float* sc = score + (size_t)b * h * w;
+    const float NEG = -INFINITY;
+    for (int i = threadIdx.x; i < NMS_REG * NMS_REG; i += blockDim.x) {
+        const int y = y0 + i / NMS_REG, x = x0 + i % NMS_REG;
+        S[i] = (y >= 0 && y < h && x >= 0 && x < w) ? sc[(size_t)y * w + x] : NEG;
+    }
+    __syncthreads();
+    pool_rows(S, T, radius);
+    __syncthreads();
+    pool_cols(T, A, radius);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NMS_REG * NMS_REG; i += blockDim.x) {
+        const bool inside = S[i] != NEG;
+        M[i] = (inside && S[i] == A[i]) ? 1 : 0;
+    }
+    __syncthreads();
+    for (int it = 0; it < 2; ++it) {
+        for (int i = threadIdx.x; i < NMS_REG * NMS_REG; i += blockDim.x) F[i] = M[i] ? 1.f : 0.f;
+        __syncthreads();
+        pool_rows(F, T, radius);
+        __syncthreads();
+        pool_cols(T, A, radius);
+        __syncthreads();
+        for (int i = threadIdx.x; i < NMS_REG * NMS_REG; i += blockDim.x) {
+            const bool inside = S[i] != NEG;
+            const bool supp = A[i] > 0.f;
+            P[i] = supp ? 1 : 0;
+            F[i] = inside ? (supp ? 0.f : S[i]) : NEG;  // supp_scores
+        }
+        __syncthreads();
+        pool_rows(F, T, radius);
+        __syncthreads();
+        pool_cols(T, A, radius);
+        __syncthreads();
+        for (int i = threadIdx.x; i < NMS_REG * NMS_REG; i += blockDim.x) {
+            const bool inside = S[i] != NEG;
+            const bool newmax = inside && (F[i] == A[i]);
+            if (newmax && !P[i]) M[i] = 1;
+        }
+        __syncthreads();
+    }
+    // emit survivors of the central tile
+    for (int i = threadIdx.x; i < NMS_TILE * NMS_TILE; i += blockDim.x) {
+        const int ly = i / NMS_TILE + NMS_HALO, lx = i % NMS_TILE + NMS_HALO;
+        const int y = y0 + ly, x = x0 + lx;
+        const int j = ly * NMS_REG + lx;
+        bool keep = false;
+        float s = 0.f;
+        if (y < h && x < w) {
+            s = S[j];
+            keep = M[j] && s > threshold && y >= border && y < h - border && x >= border && x < w - border;
+        }
+        const unsigned ballot = __ballot_sync(__activemask(), keep);
+        if (keep) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(ballot) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cand_count[slot0 + b], __popc(ballot));
+            base = __shfl_sync(ballot, base, leader);
+            const int pos = base + __popc(ballot & ((1u << lane) - 1));
+            if (pos < GNB_CAND_CAP) {
+                const unsigned long long key =
+                    ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(s)) << 32) | (unsigned)(y * w + x);
+                cand_keys[(size_t)(slot0 + b) * GNB_CAND_CAP + pos] = key;
+            }
+        }
+    }
+}
+
+// One CTA per image: exact top-K of the candidate keys (radix select on the 64-bit key), then a
+// bitonic sort of the K selected keys in shared memory.
+__global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __restrict__ cand_keys,
+                                                    const int* __restrict__ cand_count, int slot0, int w, int k_cap,
+                                                    float* __restrict__ kp_xy, float* __restrict__ kp_score,
+                                                    int* __restrict__ kp_count) {
+    __shared__ unsigned long long sel[GNB_MAX_KP];
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix, s_mask;
+    __shared__ int s_remaining, s_nsel;
+    const int slot = slot0 + blockIdx.x;
+    const int n_raw = cand_count[slot];
+    if (n_raw > GNB_CAND_CAP) {  // overflow: candidates were dropped in atomic order -> refuse
+        if (threadIdx.x == 0) kp_count[slot] = -1;
+        return;
+    }
+    const int n = n_raw;
+    const unsigned long long* keys = cand_keys + (size_t)slot * GNB_CAND_CAP;
+    unsigned long long kth = ~0ull;
+    if (n > k_cap) {
+        if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_remaining = k_cap; }
+        __syncthreads();
+        for (int pass = 7; pass >= 0; --pass) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix, mask = s_mask;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const unsigned long long key = keys[i];
+                if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> (8 * pass)) & 255ull)], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int cum = 0, d = 0;
+                for (; d < 255; ++d) {
+                    if (cum + hist[d] >= s_remaining) break;
+                    cum += hist[d];
+                }
+                s_remaining -= cum;
+                s_prefix |= (unsigned long long)d << (8 * pass);
+                s_mask |= 255ull << (8 * pass);
+            }
+            __syncthreads();
+        }
+        kth = s_prefix;
+    }
+    if (threadIdx.x == 0) s_nsel = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long key = keys[i];
+        if (key <= kth) {
+            const int pos = atomicAdd(&s_nsel, 1);
+            if (pos < GNB_MAX_KP) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const int nsel = min(s_nsel, k_cap);
+    int npow = 1;
+    while (npow < nsel) npow <<= 1;
+    for (int i = nsel + threadIdx.x; i < npow; i += blockDim.x) sel[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= npow; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool up = (i & size) == 0;
+                    const unsigned long long a = sel[i], c = sel[j];
+                    if ((a > c) == up) { sel[i] = c; sel[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
+        const unsigned long long key = sel[i];
+        const unsigned idx = (unsigned)(key & 0xFFFFFFFFull);
+        const float s = __uint_as_float(0xFFFFFFFFu - (unsigned)(key >> 32));
+        kp_xy[((size_t)slot * k_cap + i) * 2 + 0] = (float)(idx % (unsigned)w);
+        kp_xy[((size_t)slot * k_cap + i) * 2 + 1] = (float)(idx / (unsigned)w);
+        kp_score[(size_t)slot * k_cap + i] = s;
+    }
+    if (threadIdx.x == 0) kp_count[slot] = nsel;
+}
+
+int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slot0) {
+    if (ctx->cfg.nms_radius * 5 > NMS_HALO) {
+        GNB_SET_ERR(ctx, "nms_radius %d too large for the NMS halo", ctx->cfg.nms_radius);
+        return GNB_E_INVALID;
+    }
+    GNB_CUDA(ctx, cudaMemsetAsync(ctx->cand_count + slot0, 0, sizeof(int) * n, ctx->stream));
+    const size_t smem = (size_t)NMS_REG * NMS_REG * (4 * sizeof(float) + 2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(w, NMS_TILE), ceil_div(h, NMS_TILE), n);
+    nms_kernel<<<grid, 256, smem, ctx->stream>>>(score, h, w, ctx->cfg.nms_radius, ctx->cfg.keypoint_threshold,
+                                                 ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count);
+    GNB_LAUNCH_CHECK(ctx);
+    topk_kernel<<<n, 1024, 0, ctx->stream>>>(ctx->cand_keys, ctx->cand_count, slot0, w, ctx->cfg.max_keypoints,
+                                             ctx->kp_xy, ctx->kp_score, ctx->kp_count);
+    GNB_LAUNCH_CHECK(ctx);
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one warp per keypoint; lane l owns channels [8l, 8l+8).  Reads 4 x 1 KB, writes 1 KB.
+__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ dense, int hc, int wc, int img_h,
+                                                     int img_w, const float* __restrict__ kp_xy,
+                                                     const int* __restrict__ kp_count, int slot0, int k_cap,
+                                                     float* __restrict__ desc) {
+    const int b = blockIdx.y;
+    const int slot = slot0 + b;
+    const int kp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (kp >= kp_count[slot]) return;
+    const float x = kp_xy[((size_t)slot * k_cap + kp) * 2 + 0], y = kp_xy[((size_t)slot * k_cap + kp) * 2 + 1];
+    // grid_sample(align_corners=True) on g = (kp - 3.5) / (dim - 4.5) * 2 - 1
+    const float gx = __fdiv_rn(__fsub_rn(x, 3.5f), (float)img_w - 4.5f);
+    const float gy = __fdiv_rn(__fsub_rn(y, 3.5f), (float)img_h - 4.5f);
+    const float fx = __fmul_rn(gx, (float)(wc - 1)), fy = __fmul_rn(gy, (float)(hc - 1));
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float ax = __fsub_rn(fx, x0f), ay = __fsub_rn(fy, y0f);
+    const float w00 = __fmul_rn(1.f - ax, 1.f - ay), w01 = __fmul_rn(ax, 1.f - ay);
+    const float w10 = __fmul_rn(1.f - ax, ay), w11 = __fmul_rn(ax, ay);
+    const float* base = dense + (size_t)b * hc * wc * 256;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    auto tap = [&](int yy, int xx, float wgt) {
+        if (yy < 0 || yy >= hc || xx < 0 || xx >= wc) return;
+        const float4* p = reinterpret_cast<const float4*>(base + ((size_t)yy * wc + xx) * 256 + lane * 8);
+        const float4 a = __ldg(p), c = __ldg(p + 1);
+        v[0] = __fadd_rn(v[0], __fmul_rn(a.x, wgt)); v[1] = __fadd_rn(v[1], __fmul_rn(a.y, wgt));
+        v[2] = __fadd_rn(v[2], __fmul_rn(a.z, wgt)); v[3] = __fadd_rn(v[3], __fmul_rn(a.w, wgt));
+        v[4] = __fadd_rn(v[4], __fmul_rn(c.x, wgt)); v[5] = __fadd_rn(v[5], __fmul_rn(c.y, wgt));
+        v[6] = __fadd_rn(v[6], __fmul_rn(c.z, wgt)); v[7] = __fadd_rn(v[7], __fmul_rn(c.w, wgt));
+    };
+    tap(y0, x0, w00); tap(y0, x0 + 1, w01); tap(y0 + 1, x0, w10); tap(y0 + 1, x0 + 1, w11);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    float4* o = reinterpret_cast<float4*>(desc + ((size_t)slot * k_cap + kp) * 256 + lane * 8);
+    o[0] = make_float4(v[0] / nrm, v[1] / nrm, v[2] / nrm, v[3] / nrm);
+    o[1] = make_float4(v[4] / nrm, v[5] / nrm, v[6] / nrm, v[7] / nrm);
+}
+
+int gnb_kp_sample(gnb_ctx* ctx, const float* dense, int n, int h, int w, int slot0) {
+    const int k = ctx->cfg.max_keypoints;
+    dim3 grid(ceil_div(k * 32, 256), n);
+    sample_kernel<<<grid, 256, 0, ctx->stream>>>(dense, h / 8, w / 8, h, w, ctx->kp_xy, ctx->kp_count, slot0, k,
+                                                 ctx->desc_f32);
+    GNB_LAUNCH_CHECK(ctx);
+    return GNB_OK;
+}

@@ -1,0 +1,69 @@
+"""KeypointMatcher — drop-in for ``self._matcher`` in PoseNode.
+
+Reference call site (ros/gisnav/gisnav/core/pose_node.py:285-287)::
+
+    dists, match_indices = self._matcher(descs_qry, descs_ref, lafs_qry, lafs_ref)
+
+with ``self._matcher = LightGlueMatcher("sift", {... "filter_threshold": 0.5 ...}).to(device).eval()``
+(pose_node.py:109-121).  Returns ``(dists [K,1] float32, idxs [K,2] int64)``; column 0 indexes the
+first descriptor set, column 1 the second (pose_node.py:296-297).  torch tensors are the
+interchange type only; CUDA tensors are consumed and produced in place (no host round trip).
+The LAF arguments are accepted and ignored: the assignment head does not use keypoint geometry
+(the positional encoder lives in the transformer layers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .context import Context, ptr
+
+
+class KeypointMatcher:
+    def __init__(self, ctx: Optional[Context] = None, **ctx_kwargs):
+        self.ctx = ctx or Context(**ctx_kwargs)
+
+    # kornia modules are chained as ``.to(device).eval()`` (pose_node.py:103-105); keep that working
+    def to(self, *_args, **_kwargs):
+        return self
+
+    def eval(self):
+        return self
+
+    def match_arrays(self, desc1: np.ndarray, desc2: np.ndarray):
+        d1 = np.ascontiguousarray(desc1, np.float32)
+        d2 = np.ascontiguousarray(desc2, np.float32)
+        if d1.ndim != 2 or d2.ndim != 2 or (d1.size and d1.shape[1] != _lib.DESC_DIM) or (d2.size and d2.shape[1] != _lib.DESC_DIM):
+            raise ValueError("descriptors must be [N,256]")
+        cap = max(1, min(d1.shape[0], d2.shape[0]))
+        idx = np.empty((cap, 2), np.int64)
+        sc = np.empty((cap,), np.float32)
+        n = C.c_int(0)
+        self.ctx.check(self.ctx._lib.gnb_match(self.ctx.handle, ptr(d1), d1.shape[0], ptr(d2), d2.shape[0], 0, ptr(idx),
+                                               ptr(sc), cap, C.byref(n)))
+        return sc[: n.value].reshape(-1, 1).copy(), idx[: n.value].copy()
+
+    def __call__(self, desc1, desc2, lafs1=None, lafs2=None, hw1=None, hw2=None):
+        import torch
+
+        if not isinstance(desc1, torch.Tensor):
+            dists, idx = self.match_arrays(np.asarray(desc1), np.asarray(desc2))
+            return torch.from_numpy(dists), torch.from_numpy(idx)
+        if desc1.is_cuda:
+            d1 = desc1.detach().to(torch.float32).contiguous()
+            d2 = desc2.detach().to(torch.float32).contiguous()
+            n1, n2 = d1.shape[0], d2.shape[0]
+            cap = max(1, min(n1, n2))
+            idx = torch.empty((cap, 2), dtype=torch.int64, device=d1.device)
+            sc = torch.empty((cap,), dtype=torch.float32, device=d1.device)
+            torch.cuda.current_stream(d1.device).synchronize()  # inputs were produced on torch's stream
+            n = C.c_int(0)
+            self.ctx.check(self.ctx._lib.gnb_match(self.ctx.handle, C.c_void_p(d1.data_ptr()), n1, C.c_void_p(d2.data_ptr()),
+                                                   n2, 1, C.c_void_p(idx.data_ptr()), C.c_void_p(sc.data_ptr()), cap,
+                                                   C.byref(n)))
+            return sc[: n.value].reshape(-1, 1), idx[: n.value]
+        dists, idx = self.match_arrays(desc1.detach().cpu().numpy(), desc2.detach().cpu().numpy())
+        return torch.from_numpy(dists), torch.from_numpy(idx)
