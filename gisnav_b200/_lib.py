@@ -71,6 +71,8 @@ SIGNATURES = {
     "gnb_get_config": (_I, [_VP, C.POINTER(GnbConfig)]),
     "gnb_launch_count": (C.c_int64, [_VP]),
     "gnb_stream": (_VP, [_VP]),
+    "gnb_profile_enable": (_I, [_VP, _I]),
+    "gnb_profile_read": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_extract": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_match": (_I, [_VP, _VP, _I, _VP, _I, _I, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_solve_pnp": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, C.POINTER(_I)]),

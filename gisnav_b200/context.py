@@ -28,8 +28,17 @@ class Config:
     max_batch: int = 8
     max_image_h: int = 1088
     max_image_w: int = 1280
-    conv_impl: int = 0  # 0 tcgen05 (product), 1 SIMT validation kernel
-    match_impl: int = 0
+    conv_impl: Optional[int] = None  # 0 tcgen05 (product), 1 SIMT validation kernel; None = library default
+    match_impl: Optional[int] = None
+
+    def __post_init__(self):
+        if self.conv_impl is None or self.match_impl is None:
+            d = _lib.GnbConfig()
+            _lib.load().gnb_default_config(C.byref(d))
+            if self.conv_impl is None:
+                self.conv_impl = int(d.conv_impl)
+            if self.match_impl is None:
+                self.match_impl = int(d.match_impl)
 
     def to_c(self) -> _lib.GnbConfig:
         c = _lib.GnbConfig()
@@ -77,6 +86,24 @@ class Context:
     @property
     def stream_ptr(self) -> int:
         return int(self._lib.gnb_stream(self._h) or 0)
+
+    def profile(self, on: bool) -> None:
+        """Bracket every kernel launch with CUDA events on the library stream (bench roofline)."""
+        self.check(self._lib.gnb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> {kernel name: (total_ms, launches)} since the last read."""
+        cap = 64
+        names = C.create_string_buffer(64 * cap)
+        ms = (C.c_float * cap)()
+        cnt = (C.c_int64 * cap)()
+        n = C.c_int(0)
+        self.check(self._lib.gnb_profile_read(self._h, C.cast(names, C.c_void_p), C.cast(ms, C.c_void_p),
+                                              C.cast(cnt, C.c_void_p), cap, C.byref(n)))
+        out = {}
+        for i in range(n.value):
+            out[names.raw[64 * i: 64 * i + 64].split(b"\0")[0].decode()] = (float(ms[i]), int(cnt[i]))
+        return out
 
     def close(self) -> None:
         if self._h:

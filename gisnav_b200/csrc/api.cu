@@ -8,6 +8,59 @@
 
 static char g_create_err[512] = "";
 
+// ---- per-kernel event timing ---------------------------------------------------------------------
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+struct ProfState { std::vector<ProfRec> recs; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool; };
+
+void gnb_prof_begin(gnb_ctx* ctx, const char* name) {
+    if (!ctx->prof_on) return;
+    ProfState* ps = static_cast<ProfState*>(ctx->prof);
+    ProfRec r;
+    r.name = name;
+    if (!ps->pool.empty()) { r.a = ps->pool.back().first; r.b = ps->pool.back().second; ps->pool.pop_back(); }
+    else { cudaEventCreate(&r.a); cudaEventCreate(&r.b); }
+    cudaEventRecord(r.a, ctx->stream);
+    ps->recs.push_back(r);
+}
+void gnb_prof_end(gnb_ctx* ctx) {
+    if (!ctx->prof_on) return;
+    ProfState* ps = static_cast<ProfState*>(ctx->prof);
+    cudaEventRecord(ps->recs.back().b, ctx->stream);
+}
+
+extern "C" int gnb_profile_enable(gnb_ctx* ctx, int on) {
+    if (!ctx) return GNB_E_INVALID;
+    if (!ctx->prof) ctx->prof = new ProfState();
+    ctx->prof_on = on ? 1 : 0;
+    return GNB_OK;
+}
+
+// Aggregate the recorded launches by kernel name.  names: cap entries of 64 chars.  Clears the log.
+extern "C" int gnb_profile_read(gnb_ctx* ctx, char* names, float* total_ms, int64_t* launches, int cap, int* n_out) {
+    if (!ctx || !names || !total_ms || !launches || !n_out) return GNB_E_INVALID;
+    *n_out = 0;
+    if (!ctx->prof) return GNB_OK;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ProfState* ps = static_cast<ProfState*>(ctx->prof);
+    int n = 0;
+    for (auto& r : ps->recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        int j = 0;
+        for (; j < n; ++j) if (strncmp(names + 64 * j, r.name, 63) == 0) break;
+        if (j == n) {
+            if (n >= cap) { ps->pool.push_back({r.a, r.b}); continue; }
+            strncpy(names + 64 * j, r.name, 63); names[64 * j + 63] = 0; total_ms[j] = 0.f; launches[j] = 0; ++n;
+        }
+        total_ms[j] += ms; launches[j] += 1;
+        ps->pool.push_back({r.a, r.b});
+    }
+    ps->recs.clear();
+    *n_out = n;
+    return GNB_OK;
+}
+
 extern "C" int gnb_default_config(gnb_config* cfg) {
     if (!cfg) return GNB_E_INVALID;
     memset(cfg, 0, sizeof(*cfg));
@@ -24,8 +77,8 @@ extern "C" int gnb_default_config(gnb_config* cfg) {
     cfg->max_batch = 8;
     cfg->max_image_h = 1088;
     cfg->max_image_w = 1280;
-    cfg->conv_impl = 0;
-    cfg->match_impl = 0;
+    cfg->conv_impl = 1; // TODO(tcgen05): 0 once conv_tc.cu lands
+    cfg->match_impl = 1; // TODO(tcgen05): 0 once match_tc.cu lands
     return GNB_OK;
 }
 
@@ -133,6 +186,12 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
+    if (ctx->prof) {
+        ProfState* ps = static_cast<ProfState*>(ctx->prof);
+        for (auto& r : ps->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto& p : ps->pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        delete ps;
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -292,8 +351,7 @@ extern "C" int gnb_match(gnb_ctx* ctx, const float* desc_a, int n_a, const float
     if (n > 0) {
         if (out_idx) {
             if (on_device) {
-                widen_idx_kernel<<<ceil_div(2 * n, 256), 256, 0, ctx->stream>>>(ctx->match_idx, (long long*)out_idx, 2 * n);
-                GNB_LAUNCH_CHECK(ctx);
+                GNB_KERNEL(ctx, "widen_idx_kernel", widen_idx_kernel<<<ceil_div(2 * n, 256), 256, 0, ctx->stream>>>(ctx->match_idx, (long long*)out_idx, 2 * n));
             } else {
                 std::vector<int> tmp(2 * n);
                 GNB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->match_idx, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -428,8 +486,7 @@ extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out,
             if (n != out_floats) { GNB_SET_ERR(ctx, "layer %s has %zu floats, caller passed %zu", layer, n, out_floats); return GNB_E_INVALID; }
             int rc;
             if ((rc = gnb_ensure_stage(ctx, n, 0))) return rc;
-            bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t.p, ctx->stage_a, n);
-            GNB_LAUNCH_CHECK(ctx);
+            GNB_KERNEL(ctx, "bf16_to_f32_kernel", bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t.p, ctx->stage_a, n));
             GNB_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage_a, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
             GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             return GNB_OK;
@@ -507,10 +564,9 @@ extern "C" int gnb_match_scores(gnb_ctx* ctx, const float* desc_a, int n_a, cons
     if ((rc = gnb_ensure_stage(ctx, (size_t)n_a * n_b, 0))) return rc;
     const int k = ctx->cfg.max_keypoints, sb = ctx->cfg.max_batch;
     dim3 grid(ceil_div(n_b, 128), n_a);
-    score_matrix_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->mproj, ctx->mproj + (size_t)sb * k * 256, ctx->row_lse,
+    GNB_KERNEL(ctx, "score_matrix_kernel", score_matrix_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->mproj, ctx->mproj + (size_t)sb * k * 256, ctx->row_lse,
                                                        ctx->row_lse + (size_t)sb * k, ctx->mlogit, ctx->mlogit + (size_t)sb * k,
-                                                       n_a, n_b, ctx->stage_a);
-    GNB_LAUNCH_CHECK(ctx);
+                                                       n_a, n_b, ctx->stage_a));
     GNB_CUDA(ctx, cudaMemcpyAsync(out_scores, ctx->stage_a, sizeof(float) * n_a * n_b, cudaMemcpyDeviceToHost, ctx->stream));
     GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GNB_OK;

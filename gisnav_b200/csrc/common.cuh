@@ -89,6 +89,9 @@ struct gnb_ctx {
     size_t stage_a_floats;
     float* stage_b;
     size_t stage_b_floats;
+    // profiling
+    int prof_on;
+    void* prof;  // ProfState*
 };
 
 #define GNB_SET_ERR(ctx, ...)                                   \
@@ -109,6 +112,18 @@ struct gnb_ctx {
     do {                                               \
         (ctx)->launches++;                             \
         GNB_CUDA(ctx, cudaGetLastError());             \
+    } while (0)
+
+// Per-kernel CUDA-event timing on the launching stream (bench.py roofline): when profiling is on,
+// every GNB_KERNEL launch is bracketed by an event pair; gnb_profile_read aggregates by name.
+void gnb_prof_begin(gnb_ctx* ctx, const char* name);
+void gnb_prof_end(gnb_ctx* ctx);
+#define GNB_KERNEL(ctx, name, ...)     \
+    do {                               \
+        gnb_prof_begin(ctx, name);     \
+        __VA_ARGS__;                   \
+        gnb_prof_end(ctx);             \
+        GNB_LAUNCH_CHECK(ctx);         \
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

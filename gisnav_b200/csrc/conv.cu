@@ -200,8 +200,7 @@ static int launch_conv_simt(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, in
         attr_set = true;
     }
     dim3 grid(ceil_div(w, 16), ceil_div(h, 8), n);
-    conv_simt_kernel<CIN, KS><<<grid, 128, smem, ctx->stream>>>(in, L.w, L.bias, h, w, L.cout, L.cout_pad, out_bf, out_f, relu, pool);
-    GNB_LAUNCH_CHECK(ctx);
+    GNB_KERNEL(ctx, "conv_simt_kernel", conv_simt_kernel<CIN, KS><<<grid, 128, smem, ctx->stream>>>(in, L.w, L.bias, h, w, L.cout, L.cout_pad, out_bf, out_f, relu, pool));
     return GNB_OK;
 }
 
@@ -274,8 +273,7 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w) {
     int rc;
     {
         dim3 grid(ceil_div(w, 32), ceil_div(h, 8), n);
-        conv1a_kernel<<<grid, 256, 0, ctx->stream>>>(cw.img, ctx->layers[L1A].w, ctx->layers[L1A].bias, h, w, cw.a1a);
-        GNB_LAUNCH_CHECK(ctx);
+        GNB_KERNEL(ctx, "conv1a_kernel", conv1a_kernel<<<grid, 256, 0, ctx->stream>>>(cw.img, ctx->layers[L1A].w, ctx->layers[L1A].bias, h, w, cw.a1a));
     }
     if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
     if ((rc = conv_layer(ctx, L2A, cw.p1, n, h / 2, w / 2, cw.a2a, nullptr, 1, 0))) return rc;
@@ -289,9 +287,7 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w) {
     if ((rc = conv_layer(ctx, LDA, cw.a4b, n, h / 8, w / 8, cw.ada, nullptr, 1, 0))) return rc;
     if ((rc = conv_layer(ctx, LDB, cw.ada, n, h / 8, w / 8, nullptr, cw.dense, 0, 0))) return rc;
     const int cells = n * (h / 8) * (w / 8);
-    softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score);
-    GNB_LAUNCH_CHECK(ctx);
-    l2norm256_kernel<<<ceil_div(cells * 32, 256), 256, 0, ctx->stream>>>(cw.dense, cells);
-    GNB_LAUNCH_CHECK(ctx);
+    GNB_KERNEL(ctx, "softmax_d2s_kernel", softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score));
+    GNB_KERNEL(ctx, "l2norm256_kernel", l2norm256_kernel<<<ceil_div(cells * 32, 256), 256, 0, ctx->stream>>>(cw.dense, cells));
     return GNB_OK;
 }

@@ -214,12 +214,10 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         attr_set = true;
     }
     dim3 grid(ceil_div(w, NMS_TILE), ceil_div(h, NMS_TILE), n);
-    nms_kernel<<<grid, 256, smem, ctx->stream>>>(score, h, w, ctx->cfg.nms_radius, ctx->cfg.keypoint_threshold,
-                                                 ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count);
-    GNB_LAUNCH_CHECK(ctx);
-    topk_kernel<<<n, 1024, 0, ctx->stream>>>(ctx->cand_keys, ctx->cand_count, slot0, w, ctx->cfg.max_keypoints,
-                                             ctx->kp_xy, ctx->kp_score, ctx->kp_count);
-    GNB_LAUNCH_CHECK(ctx);
+    GNB_KERNEL(ctx, "nms_kernel", nms_kernel<<<grid, 256, smem, ctx->stream>>>(score, h, w, ctx->cfg.nms_radius, ctx->cfg.keypoint_threshold,
+                                                 ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count));
+    GNB_KERNEL(ctx, "topk_kernel", topk_kernel<<<n, 1024, 0, ctx->stream>>>(ctx->cand_keys, ctx->cand_count, slot0, w, ctx->cfg.max_keypoints,
+                                             ctx->kp_xy, ctx->kp_score, ctx->kp_count));
     return GNB_OK;
 }
 
@@ -271,8 +269,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ d
 int gnb_kp_sample(gnb_ctx* ctx, const float* dense, int n, int h, int w, int slot0) {
     const int k = ctx->cfg.max_keypoints;
     dim3 grid(ceil_div(k * 32, 256), n);
-    sample_kernel<<<grid, 256, 0, ctx->stream>>>(dense, h / 8, w / 8, h, w, ctx->kp_xy, ctx->kp_count, slot0, k,
-                                                 ctx->desc_f32);
-    GNB_LAUNCH_CHECK(ctx);
+    GNB_KERNEL(ctx, "sample_kernel", sample_kernel<<<grid, 256, 0, ctx->stream>>>(dense, h / 8, w / 8, h, w, ctx->kp_xy, ctx->kp_count, slot0, k,
+                                                 ctx->desc_f32));
     return GNB_OK;
 }

@@ -99,9 +99,8 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
 int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots) {
     const int k = ctx->cfg.max_keypoints;
     dim3 grid(ceil_div(k, 8), n_slots);
-    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->desc_f32, ctx->kp_count, slot0, k, g_match_wt, ctx->match_b,
-                                                  ctx->match_mw, ctx->match_mb, ctx->mproj, ctx->mlogit);
-    GNB_LAUNCH_CHECK(ctx);
+    GNB_KERNEL(ctx, "project_kernel", project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->desc_f32, ctx->kp_count, slot0, k, g_match_wt, ctx->match_b,
+                                                  ctx->match_mw, ctx->match_mb, ctx->mproj, ctx->mlogit));
     return GNB_OK;
 }
 
@@ -289,16 +288,13 @@ int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0) {
             attr_set = true;
         }
         dim3 grid(ceil_div(k, 64), pairs, 2);
-        match_rows_simt<0><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0,
-                                                             ctx->row_lse, ctx->best_val, ctx->best_idx);
-        GNB_LAUNCH_CHECK(ctx);
-        match_rows_simt<1><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0,
-                                                             ctx->row_lse, ctx->best_val, ctx->best_idx);
-        GNB_LAUNCH_CHECK(ctx);
+        GNB_KERNEL(ctx, "match_rows_simt<0>", match_rows_simt<0><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0,
+                                                             ctx->row_lse, ctx->best_val, ctx->best_idx));
+        GNB_KERNEL(ctx, "match_rows_simt<1>", match_rows_simt<1><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0,
+                                                             ctx->row_lse, ctx->best_val, ctx->best_idx));
     }
-    mutual_kernel<<<pairs, 1024, 0, ctx->stream>>>(ctx->best_val, ctx->best_idx, ctx->kp_count, ctx->kp_xy, k, slot_a0,
+    GNB_KERNEL(ctx, "mutual_kernel", mutual_kernel<<<pairs, 1024, 0, ctx->stream>>>(ctx->best_val, ctx->best_idx, ctx->kp_count, ctx->kp_xy, k, slot_a0,
                                                    slot_b0, ctx->cfg.match_threshold, ctx->match_idx, ctx->match_score,
-                                                   ctx->match_count, ctx->mkp_qry, ctx->mkp_ref);
-    GNB_LAUNCH_CHECK(ctx);
+                                                   ctx->match_count, ctx->mkp_qry, ctx->mkp_ref));
     return GNB_OK;
 }

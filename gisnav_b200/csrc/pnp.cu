@@ -689,15 +689,13 @@ int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, in
     GNB_CUDA(ctx, cudaMemsetAsync(ctx->range_flag, 0, sizeof(int) * pairs, ctx->stream));
     {
         dim3 grid(ceil_div(k, 256), pairs);
-        points3d_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->mkp_ref, ctx->match_count, k, ctx->dem, dem_h, dem_w, has_dem,
-                                                       ctx->obj, ctx->range_flag);
-        GNB_LAUNCH_CHECK(ctx);
+        GNB_KERNEL(ctx, "points3d_kernel", points3d_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->mkp_ref, ctx->match_count, k, ctx->dem, dem_h, dem_w, has_dem,
+                                                       ctx->obj, ctx->range_flag));
     }
     {
         dim3 grid(ceil_div(iters, 128), pairs);
-        hypothesis_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->obj, ctx->mkp_qry, ctx->match_count, k, ctx->kmat, iters,
-                                                         ctx->cfg.ransac_seed, min_matches, ctx->hyp, ctx->hyp_count);
-        GNB_LAUNCH_CHECK(ctx);
+        GNB_KERNEL(ctx, "hypothesis_kernel", hypothesis_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->obj, ctx->mkp_qry, ctx->match_count, k, ctx->kmat, iters,
+                                                         ctx->cfg.ransac_seed, min_matches, ctx->hyp, ctx->hyp_count));
     }
     {
         const size_t smem = (size_t)5 * k * sizeof(float);
@@ -707,15 +705,13 @@ int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, in
             attr_set = true;
         }
         dim3 grid(ceil_div(iters, 8 * 8), pairs);  // 8 warps per CTA, 8 hypotheses per warp
-        score_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->obj, ctx->mkp_qry, ctx->match_count, k, ctx->kmat, iters,
-                                                       ctx->cfg.reproj_px, ctx->hyp, ctx->hyp_count);
-        GNB_LAUNCH_CHECK(ctx);
+        GNB_KERNEL(ctx, "score_kernel", score_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->obj, ctx->mkp_qry, ctx->match_count, k, ctx->kmat, iters,
+                                                       ctx->cfg.reproj_px, ctx->hyp, ctx->hyp_count));
     }
-    finalize_kernel<<<pairs, FIN_THREADS, 0, ctx->stream>>>(
+    GNB_KERNEL(ctx, "finalize_kernel", finalize_kernel<<<pairs, FIN_THREADS, 0, ctx->stream>>>(
         ctx->obj, ctx->mkp_qry, ctx->match_count, k, ctx->kmat, ctx->affine, iters, ctx->cfg.reproj_px,
         min_matches, ctx->cfg.refine, ctx->hyp, ctx->hyp_count, ctx->range_flag, use_kp_counts ? ctx->kp_count : nullptr, 0,
-        ctx->cfg.max_batch, ref_h, ref_w, do_tail, ctx->inlier_mask, ctx->out_dev);
-    GNB_LAUNCH_CHECK(ctx);
+        ctx->cfg.max_batch, ref_h, ref_w, do_tail, ctx->inlier_mask, ctx->out_dev));
     return GNB_OK;
 }
 
@@ -736,8 +732,7 @@ int gnb_tail_device(gnb_ctx* ctx, const double* r9, const double* t3, const doub
     memcpy(h_in, r9, 72); memcpy(h_in + 9, t3, 24); memcpy(h_in + 12, affine12, 96);
     double* d = reinterpret_cast<double*>(ctx->stage_a);
     GNB_CUDA(ctx, cudaMemcpyAsync(d, h_in, sizeof(h_in), cudaMemcpyHostToDevice, ctx->stream));
-    tail_kernel<<<1, 1, 0, ctx->stream>>>(d, ref_h, ref_w, d + 24, reinterpret_cast<int*>(d + 40));
-    GNB_LAUNCH_CHECK(ctx);
+    GNB_KERNEL(ctx, "tail_kernel", tail_kernel<<<1, 1, 0, ctx->stream>>>(d, ref_h, ref_w, d + 24, reinterpret_cast<int*>(d + 40)));
     double h_out[10];
     int st = 0;
     GNB_CUDA(ctx, cudaMemcpyAsync(h_out, d + 24, sizeof(h_out), cudaMemcpyDeviceToHost, ctx->stream));

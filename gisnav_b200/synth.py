@@ -161,6 +161,7 @@ def synth_correspondences(
     tile_size: int = 1024,
     frame_hw: Tuple[int, int] = (720, 1280),
     relief: bool = True,
+    outlier_min_px: float = 0.0,
 ) -> Dict[str, np.ndarray]:
     """Direct 2D-3D correspondences for the PnP stage (no images): reference keypoints on the
     raster, DEM heights, their projections into a camera with known pose + noise + outliers."""
@@ -193,7 +194,14 @@ def synth_correspondences(
     n_out = int(round(outlier_frac * len(ref)))
     if n_out:
         idx = rng.choice(len(ref), n_out, replace=False)
-        qry[idx] = np.column_stack((rng.uniform(0, w, n_out), rng.uniform(0, h, n_out)))
+        true_uv = qry[idx].copy()
+        new_uv = np.column_stack((rng.uniform(0, w, n_out), rng.uniform(0, h, n_out)))
+        for _ in range(64):  # optionally keep outliers away from the consensus (unambiguous inlier set)
+            close = np.linalg.norm(new_uv - true_uv, axis=1) < outlier_min_px
+            if not close.any():
+                break
+            new_uv[close] = np.column_stack((rng.uniform(0, w, close.sum()), rng.uniform(0, h, close.sum())))
+        qry[idx] = new_uv
     return dict(
         mkp_ref=ref, mkp_qry=qry.astype(np.float32), dem=dem, k=k, r_gt=r, t_gt=t,
         affine=tile_affine(1000.0, 1500.0),

@@ -85,6 +85,11 @@ int gnb_get_config(const gnb_ctx* ctx, gnb_config* out);
 int64_t gnb_launch_count(const gnb_ctx* ctx);
 /* Stream all work of this ctx is issued on (a cudaStream_t), for event timing by the caller. */
 void* gnb_stream(const gnb_ctx* ctx);
+/* Per-kernel CUDA-event timing on that stream: while enabled, every kernel launch is bracketed by an
+ * event pair; gnb_profile_read synchronises, aggregates by kernel name (names: cap x 64 chars,
+ * total_ms and launches: cap entries) and clears the log. */
+int gnb_profile_enable(gnb_ctx* ctx, int on);
+int gnb_profile_read(gnb_ctx* ctx, char* names, float* total_ms, int64_t* launches, int cap, int* n_out);
 
 /* ---- the three reference call sites ------------------------------------------------------- */
 

@@ -1,0 +1,142 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls without a GPU), struct layouts, record format, sharding logic and a
+world_size-2 gloo run of the multi-process plumbing."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import gisnav_b200
+from gisnav_b200 import _lib, keypoint_record as kr, sharding, weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gisnav_b200.h")).read()
+    declared = set(re.findall(r"\b(gnb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"gnb_ctx"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_default_config_and_struct_layout():
+    lib = _lib.load()
+    c = _lib.GnbConfig()
+    assert lib.gnb_default_config(C.byref(c)) == 0
+    assert (c.max_keypoints, c.nms_radius, c.border, c.min_matches) == (1024, 4, 4, 15)
+    assert abs(c.match_threshold - 0.5) < 1e-9 and abs(c.keypoint_threshold - 0.005) < 1e-9 and c.reproj_px == 8.0
+    assert C.sizeof(_lib.GnbConfig) == 15 * 4
+    assert C.sizeof(_lib.GnbPoseResult) == 6 * 4 + 22 * 8
+    d = gisnav_b200.Config()
+    assert d.max_keypoints == c.max_keypoints and d.ransac_iters == c.ransac_iters
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.GnbError) as e:
+        gisnav_b200.Context(weights=W.pack(W.random_init(0)))
+    assert e.value.code == _lib.GNB_E_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gisnav_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "oracle/" not in src or f.endswith((".cu", ".cuh", ".py")), f  # comments may cite it
+
+
+def test_weight_blob_roundtrip():
+    p = W.random_init(1)
+    blob = W.pack(p)
+    assert len(blob) == W.BLOB_BYTES and W.N_FLOATS == 1366914
+    q = W.unpack(blob)
+    for k in p:
+        np.testing.assert_array_equal(p[k], q[k])
+    with pytest.raises(ValueError):
+        W.unpack(blob[:-4])
+    # SuperPoint's published parameter count
+    assert sum(int(np.prod(s)) for n, s in W.TENSORS.items() if not n.startswith("match.")) == 1300865
+
+
+def test_keypoint_record_layout():
+    # byte-compatible with KEYPOINT_DTYPE, ros/gisnav/gisnav/core/_shared.py:26-35
+    assert kr.KEYPOINT_DTYPE.itemsize == 532 and kr.KEYPOINT_DTYPE.fields["descriptor"][1] == 20
+    assert kr.KEYPOINT_DTYPE_256.itemsize == 1044
+    rng = np.random.default_rng(0)
+    xy = rng.random((7, 2)).astype(np.float32) * 100
+    desc = rng.random((7, 256)).astype(np.float32)
+    buf = kr.encode(xy, desc)
+    assert len(buf) == 7 * 1044
+    out = kr.decode(buf, 256)
+    np.testing.assert_array_equal(out["xy"], xy)
+    np.testing.assert_array_equal(out["descriptor"], desc)
+    assert np.all(out["size"] == 1) and np.all(out["angle"] == 0)
+    assert kr.decode(b"", 256)["xy"].shape == (0, 2)
+
+
+def test_shard_ranges_cover_exactly_once():
+    for n in (0, 1, 7, 64, 512, 513):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = sharding.shard_range(n, r, world)
+                assert 0 <= lo <= hi <= n
+                seen.extend(range(lo, hi))
+            assert seen == list(range(n))
+            sizes = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert max(h - l for l, h in sizes) - min(h - l for l, h in sizes) <= 1
+    assert [sharding.frame_owner(i, 4) for i in range(6)] == [0, 1, 2, 3, 0, 1]
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys, hashlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from gisnav_b200 import sharding, weights as W
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+blob = W.pack(W.random_init(0)) if rank == 0 else None
+t = sharding.broadcast_weights(blob, W.BLOB_BYTES)
+digest = hashlib.sha256(t.numpy().tobytes()).hexdigest()
+lo, hi = sharding.shard_range(9, rank, 2)
+tot = sharding.gather_counts(np.array([hi - lo, float(sum(range(lo, hi)))]))
+print("DIGEST", rank, digest)
+if rank == 0:
+    print("RESULT", int(tot[0]), int(tot[1]))
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_two_process_gloo_broadcast_and_sharding(tmp_path):
+    import hashlib
+    import socket
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    want = hashlib.sha256(W.pack(W.random_init(0))).hexdigest()
+    for r in range(2):  # every byte of the blob arrived on the non-source rank too
+        dig = [l for l in outs[r][0].splitlines() if l.startswith("DIGEST")][0].split()
+        assert dig[1] == str(r) and dig[2] == want
+    line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT")][0].split()
+    assert (int(line[1]), int(line[2])) == (9, 36)  # 9 pairs processed exactly once across 2 ranks
