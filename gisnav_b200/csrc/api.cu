@@ -41,7 +41,7 @@ extern "C" int gnb_profile_read(gnb_ctx* ctx, char* names, float* total_ms, int6
     *n_out = 0;
     if (!ctx->prof) return GNB_OK;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     ProfState* ps = static_cast<ProfState*>(ctx->prof);
     int n = 0;
     for (auto& r : ps->recs) {
@@ -77,8 +77,8 @@ extern "C" int gnb_default_config(gnb_config* cfg) {
     cfg->max_batch = 8;
     cfg->max_image_h = 1088;
     cfg->max_image_w = 1280;
-    cfg->conv_impl = 1; // TODO(tcgen05): 0 once conv_tc.cu lands
-    cfg->match_impl = 1; // TODO(tcgen05): 0 once match_tc.cu lands
+    cfg->conv_impl = 0;   // tcgen05 implicit GEMM
+    cfg->match_impl = 0;  // tcgen05 descriptor GEMM
     return GNB_OK;
 }
 
@@ -283,7 +283,7 @@ static int check_image(gnb_ctx* ctx, int h, int w) {
 
 static int read_count(gnb_ctx* ctx, const int* dptr, int* out) {
     GNB_CUDA(ctx, cudaMemcpyAsync(out, dptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     return GNB_OK;
 }
 
@@ -307,7 +307,7 @@ extern "C" int gnb_extract(gnb_ctx* ctx, const uint8_t* image, int h, int w, int
         if (out_xy) GNB_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->kp_xy, sizeof(float) * 2 * n, kind_out(on_device), ctx->stream));
         if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->kp_score, sizeof(float) * n, kind_out(on_device), ctx->stream));
         if (out_desc) GNB_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->desc_f32, sizeof(float) * 256 * n, kind_out(on_device), ctx->stream));
-        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GNB_SYNC(ctx);
     }
     return GNB_OK;
 }
@@ -327,7 +327,7 @@ static int load_descs(gnb_ctx* ctx, const float* desc_a, int n_a, const float* d
     if (n_b) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->desc_f32 + (size_t)sb * k * 256, desc_b, sizeof(float) * 256 * n_b, kind_in(on_device), ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n_a, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count + sb, &n_b, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // n_a/n_b live on the caller's stack
+    GNB_SYNC(ctx);  // n_a/n_b live on the caller's stack
     int rc;
     if ((rc = gnb_match_project(ctx, 0, 1))) return rc;
     if ((rc = gnb_match_project(ctx, sb, 1))) return rc;
@@ -355,12 +355,12 @@ extern "C" int gnb_match(gnb_ctx* ctx, const float* desc_a, int n_a, const float
             } else {
                 std::vector<int> tmp(2 * n);
                 GNB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->match_idx, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
-                GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                GNB_SYNC(ctx);
                 for (int i = 0; i < 2 * n; ++i) out_idx[i] = tmp[i];
             }
         }
         if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->match_score, sizeof(float) * n, kind_out(on_device), ctx->stream));
-        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GNB_SYNC(ctx);
     }
     return GNB_OK;
 }
@@ -386,11 +386,11 @@ extern "C" int gnb_solve_pnp(gnb_ctx* ctx, const float* mkp_qry, const float* mk
     if (dem) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dem, (size_t)dem_h * dem_w, kind_in(on_device), ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kmat, k9, sizeof(double) * 9, kind_in(on_device), ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->match_count, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     int rc;
     if ((rc = gnb_pnp_pairs(ctx, 1, dem_h, dem_w, dem ? 1 : 0, 0, 0, 0, 4, 0))) return rc;
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut), cudaMemcpyDeviceToHost, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     const PairOut& p = ctx->out_host[0];
     if (p.status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM raster"); return GNB_E_RANGE; }
     if (n_inliers) *n_inliers = p.n_inliers;
@@ -398,7 +398,7 @@ extern "C" int gnb_solve_pnp(gnb_ctx* ctx, const float* mkp_qry, const float* mk
     if (out_t3) memcpy(out_t3, p.t, sizeof(p.t));
     if (out_inlier_mask) {
         GNB_CUDA(ctx, cudaMemcpyAsync(out_inlier_mask, ctx->inlier_mask, n, kind_out(on_device), ctx->stream));
-        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GNB_SYNC(ctx);
     }
     return p.status;
 }
@@ -439,7 +439,7 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
     if ((rc = gnb_match_pairs(ctx, batch, 0, sb))) return rc;
     if ((rc = gnb_pnp_pairs(ctx, batch, ht, wt, dems ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1))) return rc;
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut) * batch, cudaMemcpyDeviceToHost, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     for (int b = 0; b < batch; ++b) {
         pairout_to_result(ctx->out_host[b], &results[b]);
         if (results[b].n_kp_qry < 0 || results[b].n_kp_ref < 0) {
@@ -462,7 +462,7 @@ extern "C" int gnb_dense(gnb_ctx* ctx, const uint8_t* image, int h, int w, int s
     if ((rc = gnb_conv_forward(ctx, 1, h, w))) return rc;
     if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->cw.score, sizeof(float) * h * w, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_dense) GNB_CUDA(ctx, cudaMemcpyAsync(out_dense, ctx->cw.dense, sizeof(float) * (h / 8) * (w / 8) * 256, cudaMemcpyDeviceToHost, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     return GNB_OK;
 }
 
@@ -488,7 +488,7 @@ extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out,
             if ((rc = gnb_ensure_stage(ctx, n, 0))) return rc;
             GNB_KERNEL(ctx, "bf16_to_f32_kernel", bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t.p, ctx->stage_a, n));
             GNB_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage_a, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-            GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            GNB_SYNC(ctx);
             return GNB_OK;
         }
     }
@@ -496,7 +496,7 @@ extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out,
         const size_t n = (size_t)(cw.h / 8) * (cw.w / 8) * 65;
         if (n != out_floats) return GNB_E_INVALID;
         GNB_CUDA(ctx, cudaMemcpyAsync(out, cw.semi, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GNB_SYNC(ctx);
         return GNB_OK;
     }
     GNB_SET_ERR(ctx, "unknown layer '%s'", layer);
@@ -519,7 +519,7 @@ extern "C" int gnb_select_keypoints(gnb_ctx* ctx, const float* score, int h, int
     if (n > 0) {
         if (out_xy) GNB_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->kp_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
         if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->kp_score, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GNB_SYNC(ctx);
     }
     return GNB_OK;
 }
@@ -533,13 +533,13 @@ extern "C" int gnb_sample_descriptors(gnb_ctx* ctx, const float* dense, int hc, 
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.dense, dense, sizeof(float) * hc * wc * 256, cudaMemcpyHostToDevice, ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_xy, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     // the sampler derives hc,wc from the image size; honour the caller's explicit map size
     if (hc != img_h / 8 || wc != img_w / 8) { GNB_SET_ERR(ctx, "dense map must be image/8"); return GNB_E_INVALID; }
     int rc;
     if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, 1, img_h, img_w, 0))) return rc;
     GNB_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->desc_f32, sizeof(float) * 256 * n, cudaMemcpyDeviceToHost, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     return GNB_OK;
 }
 
@@ -568,7 +568,7 @@ extern "C" int gnb_match_scores(gnb_ctx* ctx, const float* desc_a, int n_a, cons
                                                        ctx->row_lse + (size_t)sb * k, ctx->mlogit, ctx->mlogit + (size_t)sb * k,
                                                        n_a, n_b, ctx->stage_a));
     GNB_CUDA(ctx, cudaMemcpyAsync(out_scores, ctx->stage_a, sizeof(float) * n_a * n_b, cudaMemcpyDeviceToHost, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     return GNB_OK;
 }
 
@@ -578,7 +578,7 @@ extern "C" int gnb_ransac_debug(gnb_ctx* ctx, int32_t* out_counts, float* out_hy
     const int it = ctx->cfg.ransac_iters;
     if (out_counts) GNB_CUDA(ctx, cudaMemcpyAsync(out_counts, ctx->hyp_count, sizeof(int) * it, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_hyp) GNB_CUDA(ctx, cudaMemcpyAsync(out_hyp, ctx->hyp, sizeof(float) * 12 * it, cudaMemcpyDeviceToHost, ctx->stream));
-    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GNB_SYNC(ctx);
     if (out_best) *out_best = ctx->out_host[0].best_hypothesis;
     return GNB_OK;
 }

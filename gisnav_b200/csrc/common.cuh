@@ -40,6 +40,9 @@ struct PairOut {
     double r[9], t[3], ecef[3], quat[4], lla[3];
 };
 
+struct gnb_ctx;
+int gnb_tc_err_check(gnb_ctx* ctx);  // after a stream sync: did a bounded tcgen05 pipeline wait time out?
+
 struct gnb_ctx {
     gnb_config cfg;
     int device;
@@ -124,6 +127,14 @@ void gnb_prof_end(gnb_ctx* ctx);
         __VA_ARGS__;                   \
         gnb_prof_end(ctx);             \
         GNB_LAUNCH_CHECK(ctx);         \
+    } while (0)
+
+// stream sync + check of the tcgen05 pipeline watchdog word
+#define GNB_SYNC(ctx)                                              \
+    do {                                                           \
+        GNB_CUDA(ctx, cudaStreamSynchronize((ctx)->stream));       \
+        int _rc = gnb_tc_err_check(ctx);                           \
+        if (_rc) return _rc;                                       \
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -35,7 +35,7 @@ int gnb_conv_init(gnb_ctx* ctx, const float* blob) {
         const LayerSpec& s = kSpecs[l];
         ConvLayer& L = ctx->layers[l];
         L.cin = s.cin; L.cout = s.cout; L.ks = s.ks;
-        L.cout_pad = (s.cout + 15) / 16 * 16;
+        L.cout_pad = (s.cout + 31) / 32 * 32;  // tcgen05 epilogue reads 32 columns at a time
         const int taps = s.ks * s.ks;
         const float* w = blob + off;                       // [cout][cin][ks][ks]
         const float* b = w + (size_t)s.cout * s.cin * taps;  // [cout]

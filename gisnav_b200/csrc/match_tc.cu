@@ -1,4 +1,265 @@
-// match_tc.cu — tcgen05 descriptor GEMM (placeholder until the kernel lands).
-#include "common.cuh"
-int gnb_match_tc_init(gnb_ctx* ctx) { GNB_SET_ERR(ctx, "tcgen05 matcher not built"); return GNB_E_INVALID; }
-int gnb_match_tc_rowpass(gnb_ctx* ctx, int, int, int, int) { GNB_SET_ERR(ctx, "tcgen05 matcher not built"); return GNB_E_INVALID; }
+// match_tc.cu — K4 on the 5th-generation tensor cores: the descriptor GEMM S = m_a m_b^T runs as
+// tcgen05.mma (bf16 operands staged by TMA into 128B-swizzled shared memory, fp32 accumulators in
+// TMEM) with the dual-softmax statistics fused into the TMEM epilogue, so S never touches HBM.
+//
+// One CTA owns 128 rows of one side (128 TMEM lanes) and streams the other side in 128-column
+// tiles through a 2-stage TMA ring and a 2-stage TMEM accumulator ring:
+//   warp 0   TMA producer (one elected lane)        warp 1   MMA issuer (one elected lane)
+//   warp 2   TMEM allocator                         warps 4-7 epilogue: tcgen05.ld, one row per thread
+// pass 0: running (max, sum exp) per row -> row_lse.   pass 1: per-row argmax of the assignment
+// score (oracle/matcher_ref.py) -> best_val / best_idx.  The "column" statistics are the row
+// statistics of the swapped product (blockIdx.z = side), as in the SIMT validation kernel.
+#include "tc_common.cuh"
+
+#include <math.h>
+
+#define MT_BM 128          // rows per CTA
+#define MT_BN 128          // columns per tile
+#define MT_K 256           // descriptor dimension
+#define MT_KC 64           // K elements per 128-byte swizzle chunk
+#define MT_CHUNK_BYTES (128 * 128)                 // 128 rows x 128 B
+#define MT_TILE_BYTES (MT_CHUNK_BYTES * (MT_K / MT_KC))  // 64 KB: one operand tile, full K
+#define MT_STAGES 2
+#define MT_TMEM_COLS 256   // 2 accumulator stages x 128 columns
+#define MT_SMEM_BYTES (1024 + MT_TILE_BYTES * (1 + MT_STAGES) + 256 + 2 * 2 * MT_BN * 4)
+
+static CUtensorMap* g_tmap_host = nullptr;   // pinned copy kept for the kernel parameter
+static int* g_tc_err_host = nullptr;         // host-mapped error word written by timed-out waits
+static int* g_tc_err_dev = nullptr;
+
+gnb_encode_tiled_fn gnb_get_encode_tiled(gnb_ctx* ctx) {
+    static gnb_encode_tiled_fn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+        GNB_SET_ERR(ctx, "cuTensorMapEncodeTiled not available from the driver");
+        return nullptr;
+    }
+    fn = reinterpret_cast<gnb_encode_tiled_fn>(p);
+    return fn;
+}
+
+int gnb_make_tmap_bf16(gnb_ctx* ctx, CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box) {
+    gnb_encode_tiled_fn fn = gnb_get_encode_tiled(ctx);
+    if (!fn) return GNB_E_CUDA;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        GNB_SET_ERR(ctx, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+        return GNB_E_CUDA;
+    }
+    return GNB_OK;
+}
+
+int* gnb_tc_err_dev(gnb_ctx* ctx) {
+    if (!g_tc_err_host) {
+        if (cudaHostAlloc((void**)&g_tc_err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        *g_tc_err_host = 0;
+        if (cudaHostGetDevicePointer((void**)&g_tc_err_dev, g_tc_err_host, 0) != cudaSuccess) return nullptr;
+    }
+    (void)ctx;
+    return g_tc_err_dev;
+}
+int gnb_tc_err_check(gnb_ctx* ctx) {
+    if (g_tc_err_host && *g_tc_err_host) {
+        GNB_SET_ERR(ctx, "tcgen05 pipeline wait timed out (code %d)", *g_tc_err_host);
+        *g_tc_err_host = 0;
+        return GNB_E_CUDA;
+    }
+    return GNB_OK;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mlogit,
+                                                        const int* __restrict__ kp_count, int k_cap, int slot_a0, int slot_b0,
+                                                        float* __restrict__ row_lse, float* __restrict__ best_val,
+                                                        int* __restrict__ best_idx, int* err) {
+    const int pair = blockIdx.y, side = blockIdx.z;
+    const int slot_r = side == 0 ? slot_a0 + pair : slot_b0 + pair;
+    const int slot_c = side == 0 ? slot_b0 + pair : slot_a0 + pair;
+    const int nr = max(kp_count[slot_r], 0), nc = max(kp_count[slot_c], 0);
+    const int r0 = blockIdx.x * MT_BM;
+    if (r0 >= nr || nc == 0) return;  // uniform exit before any barrier / TMEM allocation
+    const int n_tiles = (nc + MT_BN - 1) / MT_BN;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                                   // 64 KB
+    uint8_t* sB = smem + MT_TILE_BYTES;                   // MT_STAGES x 64 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MT_TILE_BYTES * (1 + MT_STAGES));
+    uint64_t* a_full = bars;            // 1
+    uint64_t* b_full = bars + 1;        // [2]
+    uint64_t* b_empty = bars + 3;       // [2]
+    uint64_t* t_full = bars + 5;        // [2]
+    uint64_t* t_empty = bars + 7;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* s_cl = reinterpret_cast<float*>(smem + MT_TILE_BYTES * (1 + MT_STAGES) + 256);  // [2][128] column LSE
+    float* s_lb = s_cl + 2 * MT_BN;                                                       // [2][128] column logit
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap);
+        tc::mbar_init(a_full, 1);
+        for (int s = 0; s < MT_STAGES; ++s) {
+            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&b_empty[s], 1);
+            tc::mbar_init(&t_full[s], 1);
+            tc::mbar_init(&t_empty[s], 4);  // one arrive per epilogue warp
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, MT_TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(a_full, MT_TILE_BYTES);
+            for (int c = 0; c < MT_K / MT_KC; ++c) tc::tma_load_3d(sA + c * MT_CHUNK_BYTES, &tmap, a_full, c * MT_KC, r0, slot_r);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % MT_STAGES;
+                const uint32_t ph = (j / MT_STAGES) & 1;
+                if (j >= MT_STAGES && !tc::mbar_wait(&b_empty[s], ph ^ 1, err, 101)) break;
+                tc::mbar_arrive_expect_tx(&b_full[s], MT_TILE_BYTES);
+                for (int c = 0; c < MT_K / MT_KC; ++c)
+                    tc::tma_load_3d(sB + s * MT_TILE_BYTES + c * MT_CHUNK_BYTES, &tmap, &b_full[s], c * MT_KC, j * MT_BN, slot_c);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(MT_BM, MT_BN);
+            bool ok = tc::mbar_wait(a_full, 0, err, 102);
+            for (int j = 0; ok && j < n_tiles; ++j) {
+                const int s = j % MT_STAGES;
+                const uint32_t ph = (j / MT_STAGES) & 1;
+                if (!tc::mbar_wait(&b_full[s], ph, err, 103)) break;
+                if (j >= MT_STAGES && !tc::mbar_wait(&t_empty[s], ph ^ 1, err, 104)) break;
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * MT_BN);
+#pragma unroll
+                for (int c = 0; c < MT_K / MT_KC; ++c) {
+                    const uint32_t a_addr = tc::smem_u32(sA + c * MT_CHUNK_BYTES);
+                    const uint32_t b_addr = tc::smem_u32(sB + s * MT_TILE_BYTES + c * MT_CHUNK_BYTES);
+#pragma unroll
+                    for (int k = 0; k < MT_KC / 16; ++k) {
+                        const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 1024);
+                        const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 1024);
+                        tc::umma_bf16(d_tmem, da, db, idesc, (c | k) ? 1u : 0u);
+                    }
+                }
+                tc::umma_commit(&b_empty[s]);  // smem stage reusable once these MMAs have read it
+                tc::umma_commit(&t_full[s]);   // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread <-> TMEM lane <-> row =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row_local = q * 32 + lane;
+        const int row = r0 + row_local;
+        const int et = threadIdx.x - 128;       // 0..127 among the epilogue threads
+        float run_max = -INFINITY, run_sum = 0.f, bv = -INFINITY;
+        int bi = -1;
+        float rl = 0.f, la = 0.f;
+        if (PASS == 1 && row < nr) { rl = row_lse[(size_t)slot_r * k_cap + row]; la = mlogit[(size_t)slot_r * k_cap + row]; }
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j % MT_STAGES;
+            const uint32_t ph = (j / MT_STAGES) & 1;
+            const int c0 = j * MT_BN;
+            if (PASS == 1) {
+                const int col = c0 + et;
+                s_cl[s * MT_BN + et] = col < nc ? row_lse[(size_t)slot_c * k_cap + col] : 0.f;
+                s_lb[s * MT_BN + et] = col < nc ? mlogit[(size_t)slot_c * k_cap + col] : 0.f;
+                tc::named_bar_sync(1, 128);
+            }
+            if (!tc::mbar_wait(&t_full[s], ph, err, 105)) break;
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * MT_BN);
+#pragma unroll 1
+            for (int cc = 0; cc < MT_BN; cc += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(taddr + cc, v);
+                tc::tmem_ld_wait();
+                if (PASS == 0) {
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + cc + i < nc) m = fmaxf(m, __uint_as_float(v[i]));
+                    const float nm = fmaxf(run_max, m);
+                    float e = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + cc + i < nc) e += expf(__uint_as_float(v[i]) - nm);
+                    run_sum = run_sum * expf(run_max - nm) + e;
+                    run_max = nm;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c0 + cc + i;
+                        if (col < nc) {
+                            const float sv = __uint_as_float(v[i]);
+                            const float t_row = __fsub_rn(sv, rl), t_col = __fsub_rn(sv, s_cl[s * MT_BN + cc + i]);
+                            const float lb = s_lb[s * MT_BN + cc + i];
+                            float sc;
+                            if (side == 0) sc = __fadd_rn(__fadd_rn(__fadd_rn(t_row, t_col), la), lb);
+                            else sc = __fadd_rn(__fadd_rn(__fadd_rn(t_col, t_row), lb), la);
+                            if (sc > bv || bi < 0) { bv = sc; bi = col; }
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&t_empty[s]);
+        }
+        if (row < nr) {
+            if (PASS == 0) row_lse[(size_t)slot_r * k_cap + row] = run_max + logf(run_sum);
+            else { best_val[(size_t)slot_r * k_cap + row] = bv; best_idx[(size_t)slot_r * k_cap + row] = bi; }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, MT_TMEM_COLS);
+    }
+}
+
+int gnb_match_tc_init(gnb_ctx* ctx) {
+    if (!gnb_tc_err_dev(ctx)) { GNB_SET_ERR(ctx, "cannot allocate the host-mapped error word"); return GNB_E_CUDA; }
+    if (!g_tmap_host) g_tmap_host = new CUtensorMap();
+    const uint64_t k = (uint64_t)ctx->cfg.max_keypoints;
+    const uint64_t dims[3] = {MT_K, k, (uint64_t)ctx->kp_slots};
+    const uint64_t strides[2] = {MT_K * 2, k * MT_K * 2};
+    const uint32_t box[3] = {MT_KC, 128, 1};
+    int rc = gnb_make_tmap_bf16(ctx, g_tmap_host, ctx->mproj, 3, dims, strides, box);
+    if (rc) return rc;
+    GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
+    GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
+    return GNB_OK;
+}
+
+int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int pass) {
+    const int k = ctx->cfg.max_keypoints;
+    dim3 grid(ceil_div(k, MT_BM), pairs, 2);
+    if (pass == 0)
+        GNB_KERNEL(ctx, "match_rows_tc<0>", match_rows_tc<0><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+    else
+        GNB_KERNEL(ctx, "match_rows_tc<1>", match_rows_tc<1><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+    return GNB_OK;
+}

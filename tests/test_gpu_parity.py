@@ -309,7 +309,7 @@ def test_batch_equals_single_and_is_deterministic():
 def test_full_size_properties():
     """BASELINE config 2 shape (1280x720 frame, 1024x1024 raster): size-independent properties."""
     blob = _trained_blob()
-    ground = synth.ground_texture(2048, seed=23, n_shapes=200)
+    ground = synth.ground_texture(4096, seed=23, n_shapes=200)
     pair = synth.make_pair(ground, 0)
     cfg = Config(max_batch=1, max_keypoints=1024)
     ctx = Context(cfg, weights=blob)
