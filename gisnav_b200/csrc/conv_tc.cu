@@ -10,6 +10,8 @@
 //   warp 0  TMA producer     warp 1  MMA issuer     warp 2  TMEM allocator     warps 4-7  epilogue
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 #define CT_TH 8
 #define CT_TW 16
 #define CT_A_BYTES (128 * 128)   // 128 pixels x 64 ch x 2 B
@@ -73,26 +75,24 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(128, NPAD);
-            int it = 0;
-            for (; it < n_iters; ++it) {
-                const int s = it % CT_STAGES;
-                const uint32_t ph = (it / CT_STAGES) & 1;
-                if (!tc::mbar_wait(&full[s], ph, err, 202)) break;
-                tc::tc_fence_after();
-                const uint32_t a_addr = tc::smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + CT_A_BYTES;
+        const uint32_t idesc = tc::make_idesc_bf16(128, NPAD);
+        const uint64_t d0 = tc::make_smem_desc_sw128(tc::smem_u32(smem), 1024);
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % CT_STAGES;
+            const uint32_t ph = (it / CT_STAGES) & 1;
+            if (!tc::mbar_wait(&full[s], ph, err, 202)) break;
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint64_t da0 = d0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+                const uint64_t db0 = da0 + (uint64_t)(CT_A_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 1024);
-                    const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 1024);
-                    tc::umma_bf16(tmem_base, da, db, idesc, (it | k) ? 1u : 0u);
-                }
+                for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem_base, da0 + 2 * k, db0 + 2 * k, idesc, (it | k) ? 1u : 0u);
                 tc::umma_commit(&empty[s]);
             }
-            tc::umma_commit(acc_full);
+            __syncwarp();
         }
+        if (tc::elect_one()) tc::umma_commit(acc_full);
+        __syncwarp();
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int yl = 2 * q + (lane >> 4), xl = lane & 15;
@@ -158,9 +158,195 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const __grid_constant__ CU
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2 for Cin = 64 layers (conv1b, conv2a, conv2b, conv3a: 70 % of the stack's FLOPs):
+//   * persistent CTAs (one per SM) looping over 16 x 8 output tiles;
+//   * the layer's whole weight tensor (9 taps x Cout x 128 B) stays resident in shared memory;
+//   * ONE TMA box per tile: the 18 x 10 halo (64 ch = 128 B per pixel).  The nine tap operands are
+//     nine views of that box: the UMMA descriptor's start address is shifted by (dy*10 + dx) pixels
+//     (128 B each) and its stride-byte-offset is the halo row pitch (10 x 128 B), so row group g of
+//     the M = 128 operand is image row g of the tile.  The 128B swizzle is a function of the shared
+//     memory address, so TMA's write pattern and the shifted reads agree;
+//   * two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// L2 -> SM traffic drops from 9 x (16 KB + weights) to 22.5 KB per tile.
+#define H2_TH 16
+#define H2_TW 8
+#define H2_HH (H2_TH + 2)
+#define H2_HW (H2_TW + 2)
+#define H2_HALO_BYTES (H2_HH * H2_HW * 128)           // 23040
+#define H2_HALO_STRIDE ((H2_HALO_BYTES + 1023) / 1024 * 1024)
+
+template <int NPAD, int STAGES>
+__global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_in,
+                                                              const __grid_constant__ CUtensorMap tmap_w,
+                                                              const float* __restrict__ bias, int h, int w, int n_img, int cout,
+                                                              bf16* __restrict__ out_bf, int relu, int pool, int* err) {
+    constexpr int W_TAP_BYTES = NPAD * 128;
+    constexpr int W_BYTES = 9 * W_TAP_BYTES;
+    constexpr int TMEM_COLS = 2 * NPAD;  // 128 or 256
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * H2_HALO_STRIDE);
+    uint64_t* w_full = bars;
+    uint64_t* a_full = bars + 1;             // [STAGES]
+    uint64_t* a_empty = a_full + STAGES;     // [STAGES]
+    uint64_t* t_full = a_empty + STAGES;     // [2]
+    uint64_t* t_empty = t_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // [NPAD]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (w + H2_TW - 1) / H2_TW, tiles_y = (h + H2_TH - 1) / H2_TH;
+    const int tiles_per_img = tiles_x * tiles_y;
+    const int total = tiles_per_img * n_img;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_in);
+        tc::tma_prefetch_desc(&tmap_w);
+        tc::mbar_init(w_full, 1);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    if (threadIdx.x >= 128 && threadIdx.x - 128 < NPAD) s_bias[threadIdx.x - 128] = bias[threadIdx.x - 128];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(w_full, W_BYTES);
+            for (int t = 0; t < 9; ++t) tc::tma_load_3d(sW + t * W_TAP_BYTES, &tmap_w, w_full, 0, 0, t);
+            int i = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                if (i >= STAGES && !tc::mbar_wait(&a_empty[s], ph ^ 1, err, 211)) break;
+                const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+                const int y0 = (rem / tiles_x) * H2_TH, x0 = (rem % tiles_x) * H2_TW;
+                tc::mbar_arrive_expect_tx(&a_full[s], H2_HALO_BYTES);
+                tc::tma_load_4d(sA + s * H2_HALO_STRIDE, &tmap_in, &a_full[s], 0, x0 - 1, y0 - 1, img);
+            }
+        }
+    } else if (warp == 1) {
+        // whole warp stays converged; one elected lane issues.  Descriptors are a 64-bit base plus a
+        // compile-time constant per (tap, k-step): one add each.
+        const uint32_t idesc = tc::make_idesc_bf16(128, NPAD);
+        bool ok = tc::mbar_wait(w_full, 0, err, 212);
+        const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
+        int i = 0;
+        for (int tile = blockIdx.x; ok && tile < total; tile += gridDim.x, ++i) {
+            const int s = i % STAGES, as = i & 1;
+            if (!tc::mbar_wait(&a_full[s], (i / STAGES) & 1, err, 213)) break;
+            if (i >= 2 && !tc::mbar_wait(&t_empty[as], ((i >> 1) & 1) ^ 1, err, 214)) break;
+            tc::tc_fence_after();
+            const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * NPAD);
+            if (tc::elect_one()) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
+                        const uint64_t db = db0 + (uint64_t)((t * W_TAP_BYTES + k * 32) >> 4);
+                        tc::umma_bf16(d_tmem, da, db, idesc, (t | k) ? 1u : 0u);
+                    }
+                }
+                tc::umma_commit(&a_empty[s]);
+                tc::umma_commit(&t_full[as]);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int yl = 4 * q + (lane >> 3), xl = lane & 7;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+            const int as = i & 1;
+            const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int y = (rem / tiles_x) * H2_TH + yl, x = (rem % tiles_x) * H2_TW + xl;
+            if (!tc::mbar_wait(&t_full[as], (i >> 1) & 1, err, 215)) break;
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * NPAD);
+            const bool inside = (y < h) && (x < w);
+            size_t pix;
+            bool writer;
+            if (pool) {
+                writer = inside && ((xl | yl) & 1) == 0;
+                pix = ((size_t)img * (h / 2) + (y >> 1)) * (size_t)(w / 2) + (x >> 1);
+            } else {
+                writer = inside;
+                pix = ((size_t)img * h + y) * (size_t)w + x;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < NPAD; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(taddr + c0, v);
+                tc::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a0 = __uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j];
+                    float a1 = __uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1];
+                    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
+                    uint32_t u = *reinterpret_cast<uint32_t*>(&pk);
+                    if (pool) {  // max of bf16-rounded values == rounding of the max (monotone)
+                        __nv_bfloat162 o = pk;
+                        uint32_t u1 = __shfl_xor_sync(0xffffffffu, u, 1);
+                        o = __hmax2(o, *reinterpret_cast<__nv_bfloat162*>(&u1));
+                        u = *reinterpret_cast<uint32_t*>(&o);
+                        uint32_t u8 = __shfl_xor_sync(0xffffffffu, u, 8);
+                        o = __hmax2(o, *reinterpret_cast<__nv_bfloat162*>(&u8));
+                        u = *reinterpret_cast<uint32_t*>(&o);
+                    }
+                    packed[j] = u;
+                }
+                if (writer) {
+                    uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&t_empty[as]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int NPAD, int STAGES>
+static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
+                               bf16* out_bf, int relu, int pool, const char* name) {
+    constexpr int smem = 1024 + 9 * NPAD * 128 + STAGES * H2_HALO_STRIDE + 256 + NPAD * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_kernel<NPAD, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int total = ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n;
+    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+    GNB_KERNEL(ctx, name, conv_tc_halo_kernel<NPAD, STAGES><<<grid, 256, smem, ctx->stream>>>(
+        tin, tw, L.bias, h, w, n, L.cout, out_bf, relu, pool, gnb_tc_err_dev(ctx)));
+    return GNB_OK;
+}
+
 template <int NPAD>
 static int launch_conv_tc(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
-                          bf16* out_bf, float* out_f, int relu, int pool) {
+                          bf16* out_bf, float* out_f, int relu, int pool, const char* name) {
     constexpr int smem = CT_STAGES * (CT_A_BYTES + NPAD * 128) + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
@@ -168,7 +354,7 @@ static int launch_conv_tc(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMa
         attr_set = true;
     }
     dim3 grid(ceil_div(w, CT_TW), ceil_div(h, CT_TH), n);
-    GNB_KERNEL(ctx, "conv_tc_kernel", conv_tc_kernel<NPAD><<<grid, 256, smem, ctx->stream>>>(
+    GNB_KERNEL(ctx, name, conv_tc_kernel<NPAD><<<grid, 256, smem, ctx->stream>>>(
         tin, tw, L.bias, h, w, L.cin, L.ks, L.cout, out_bf, out_f, relu, pool, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
@@ -194,17 +380,27 @@ int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, i
     const int lid = (int)(&L - ctx->layers);
     if (lid < 0 || lid >= GNB_NUM_LAYERS || !g_wmaps[lid].valid) return GNB_E_INVALID;
     if (pool && ((h | w) & 1)) return GNB_E_INVALID;
+    static const char* kNames[GNB_NUM_LAYERS] = {"conv1a", "conv_tc:1b", "conv_tc:2a", "conv_tc:2b", "conv_tc:3a", "conv_tc:3b",
+                                                 "conv_tc:4a", "conv_tc:4b", "conv_tc:Pa", "conv_tc:Pb", "conv_tc:Da", "conv_tc:Db"};
+    static const int v1_only = getenv("GNB_CONV_TC_V1") ? atoi(getenv("GNB_CONV_TC_V1")) : 0;
     CUtensorMap tin;
     const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)L.cin * 2, (uint64_t)w * L.cin * 2, (uint64_t)h * w * L.cin * 2};
+    int rc;
+    if (!v1_only && L.cin == 64 && L.ks == 3 && out_bf && (L.cout_pad == 64 || L.cout_pad == 128)) {
+        const uint32_t hbox[4] = {64, H2_HW, H2_HH, 1};
+        if ((rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(in), 4, dims, strides, hbox))) return rc;
+        if (L.cout_pad == 64) return launch_conv_tc_halo<64, 4>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, relu, pool, kNames[lid]);
+        return launch_conv_tc_halo<128, 3>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, relu, pool, kNames[lid]);
+    }
     const uint32_t box[4] = {64, CT_TW, CT_TH, 1};
-    int rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(in), 4, dims, strides, box);
+    rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(in), 4, dims, strides, box);
     if (rc) return rc;
     switch (L.cout_pad) {
-        case 64: return launch_conv_tc<64>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool);
-        case 96: return launch_conv_tc<96>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool);
-        case 128: return launch_conv_tc<128>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool);
-        case 256: return launch_conv_tc<256>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool);
+        case 64: return launch_conv_tc<64>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool, kNames[lid]);
+        case 96: return launch_conv_tc<96>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool, kNames[lid]);
+        case 128: return launch_conv_tc<128>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool, kNames[lid]);
+        case 256: return launch_conv_tc<256>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, out_f, relu, pool, kNames[lid]);
         default: return GNB_E_INVALID;
     }
 }

@@ -117,6 +117,124 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// NMS specialised for radius 4 (the SuperPoint default): 64x64 output tile + 20 px halo = 104x104
+// region in shared memory, five separable 9-wide max filters.  Each work item owns a run of 13
+// consecutive elements of one row (or column), loads the 21 inputs it needs once and forms the
+// nine-wide maxima by doubling (m2 -> m4 -> m8 -> m9): 5 max ops and ~1.6 shared loads per output.
+// Same compare-only arithmetic as nms_kernel => bit-identical survivors.
+#define N4_TILE 64
+#define N4_REG 104
+#define N4_PITCH 105
+#define N4_RUN 13
+#define N4_THREADS 512
+
+template <bool ROWS, typename Src, typename Sink>
+__device__ __forceinline__ void n4_pass(Src src, Sink sink) {
+    const float NEG = -INFINITY;
+    for (int item = threadIdx.x; item < N4_REG * (N4_REG / N4_RUN); item += N4_THREADS) {
+        int line, run;
+        if (ROWS) { line = item / (N4_REG / N4_RUN); run = item % (N4_REG / N4_RUN); }  // adjacent lanes: same row
+        else { line = item % N4_REG; run = item / N4_REG; }                            // adjacent lanes: adjacent columns
+        const int p0 = run * N4_RUN - 4;
+        float v[N4_RUN + 8];
+#pragma unroll
+        for (int k = 0; k < N4_RUN + 8; ++k) {
+            const int p = p0 + k;
+            v[k] = (p >= 0 && p < N4_REG) ? (ROWS ? src(line, p) : src(p, line)) : NEG;
+        }
+        float m2[N4_RUN + 7], m4[N4_RUN + 5], m8[N4_RUN + 1];
+#pragma unroll
+        for (int k = 0; k < N4_RUN + 7; ++k) m2[k] = fmaxf(v[k], v[k + 1]);
+#pragma unroll
+        for (int k = 0; k < N4_RUN + 5; ++k) m4[k] = fmaxf(m2[k], m2[k + 2]);
+#pragma unroll
+        for (int k = 0; k < N4_RUN + 1; ++k) m8[k] = fmaxf(m4[k], m4[k + 4]);
+#pragma unroll
+        for (int k = 0; k < N4_RUN; ++k) {
+            const float m9 = fmaxf(m8[k], v[k + 8]);
+            const int p = run * N4_RUN + k;
+            if (ROWS) sink(line, p, m9); else sink(p, line, m9);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(N4_THREADS) nms_r4_kernel(const float* __restrict__ score, int h, int w, float threshold,
+                                                            int border, int slot0, unsigned long long* __restrict__ cand_keys,
+                                                            int* __restrict__ cand_count) {
+    extern __shared__ float sm[];
+    float* S = sm;
+    float* T = S + N4_REG * N4_PITCH;
+    float* A = T + N4_REG * N4_PITCH;
+    uint8_t* M = reinterpret_cast<uint8_t*>(A + N4_REG * N4_PITCH);
+    uint8_t* P = M + N4_REG * N4_PITCH;
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * N4_TILE - NMS_HALO, x0 = blockIdx.x * N4_TILE - NMS_HALO;
+    const float* sc = score + (size_t)b * h * w;
+    const float NEG = -INFINITY;
+    for (int i = threadIdx.x; i < N4_REG * N4_REG; i += N4_THREADS) {
+        const int ly = i / N4_REG, lx = i - ly * N4_REG;
+        const int y = y0 + ly, x = x0 + lx;
+        S[ly * N4_PITCH + lx] = (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(&sc[(size_t)y * w + x]) : NEG;
+    }
+    __syncthreads();
+    auto rdS = [&](int y, int x) { return S[y * N4_PITCH + x]; };
+    auto rdT = [&](int y, int x) { return T[y * N4_PITCH + x]; };
+    auto rdA = [&](int y, int x) { return A[y * N4_PITCH + x]; };
+    auto rdM = [&](int y, int x) { return M[y * N4_PITCH + x] ? 1.f : 0.f; };
+    auto wrT = [&](int y, int x, float v) { T[y * N4_PITCH + x] = v; };
+    n4_pass<true>(rdS, wrT);
+    __syncthreads();
+    n4_pass<false>(rdT, [&](int y, int x, float m) {
+        const float s = S[y * N4_PITCH + x];
+        M[y * N4_PITCH + x] = (s != NEG && s == m) ? 1 : 0;
+    });
+    __syncthreads();
+    for (int it = 0; it < 2; ++it) {
+        n4_pass<true>(rdM, wrT);
+        __syncthreads();
+        n4_pass<false>(rdT, [&](int y, int x, float m) {
+            const float s = S[y * N4_PITCH + x];
+            const bool supp = m > 0.f;
+            P[y * N4_PITCH + x] = supp ? 1 : 0;
+            A[y * N4_PITCH + x] = (s != NEG) ? (supp ? 0.f : s) : NEG;  // supp_scores
+        });
+        __syncthreads();
+        n4_pass<true>(rdA, wrT);
+        __syncthreads();
+        n4_pass<false>(rdT, [&](int y, int x, float m) {
+            const int j = y * N4_PITCH + x;
+            if (S[j] != NEG && A[j] == m && !P[j]) M[j] = 1;
+        });
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < N4_TILE * N4_TILE; i += N4_THREADS) {
+        const int ly = i / N4_TILE + NMS_HALO, lx = i % N4_TILE + NMS_HALO;
+        const int y = y0 + ly, x = x0 + lx;
+        const int j = ly * N4_PITCH + lx;
+        bool keep = false;
+        float s = 0.f;
+        if (y < h && x < w) {
+            s = S[j];
+            keep = M[j] && s > threshold && y >= border && y < h - border && x >= border && x < w - border;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(ballot) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cand_count[slot0 + b], __popc(ballot));
+            base = __shfl_sync(ballot, base, leader);
+            const int pos = base + __popc(ballot & ((1u << lane) - 1));
+            if (pos < GNB_CAND_CAP) {
+                const unsigned long long key =
+                    ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(s)) << 32) | (unsigned)(y * w + x);
+                cand_keys[(size_t)(slot0 + b) * GNB_CAND_CAP + pos] = key;
+            }
+        }
+    }
+}
+
 // One CTA per image: exact top-K of the candidate keys (radix select on the 64-bit key), then a
 // bitonic sort of the K selected keys in shared memory.
 __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __restrict__ cand_keys,
@@ -207,15 +325,27 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         return GNB_E_INVALID;
     }
     GNB_CUDA(ctx, cudaMemsetAsync(ctx->cand_count + slot0, 0, sizeof(int) * n, ctx->stream));
-    const size_t smem = (size_t)NMS_REG * NMS_REG * (4 * sizeof(float) + 2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    if (ctx->cfg.nms_radius == 4) {
+        const size_t smem = (size_t)N4_REG * N4_PITCH * (3 * sizeof(float) + 2);
+        static bool attr4 = false;
+        if (!attr4) {
+            GNB_CUDA(ctx, cudaFuncSetAttribute(nms_r4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr4 = true;
+        }
+        dim3 grid(ceil_div(w, N4_TILE), ceil_div(h, N4_TILE), n);
+        GNB_KERNEL(ctx, "nms_r4_kernel", nms_r4_kernel<<<grid, N4_THREADS, smem, ctx->stream>>>(
+            score, h, w, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count));
+    } else {
+        const size_t smem = (size_t)NMS_REG * NMS_REG * (4 * sizeof(float) + 2);
+        static bool attr_set = false;
+        if (!attr_set) {
+            GNB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        dim3 grid(ceil_div(w, NMS_TILE), ceil_div(h, NMS_TILE), n);
+        GNB_KERNEL(ctx, "nms_kernel", nms_kernel<<<grid, 256, smem, ctx->stream>>>(score, h, w, ctx->cfg.nms_radius, ctx->cfg.keypoint_threshold,
+                                                     ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count));
     }
-    dim3 grid(ceil_div(w, NMS_TILE), ceil_div(h, NMS_TILE), n);
-    GNB_KERNEL(ctx, "nms_kernel", nms_kernel<<<grid, 256, smem, ctx->stream>>>(score, h, w, ctx->cfg.nms_radius, ctx->cfg.keypoint_threshold,
-                                                 ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count));
     GNB_KERNEL(ctx, "topk_kernel", topk_kernel<<<n, 1024, 0, ctx->stream>>>(ctx->cand_keys, ctx->cand_count, slot0, w, ctx->cfg.max_keypoints,
                                              ctx->kp_xy, ctx->kp_score, ctx->kp_count));
     return GNB_OK;

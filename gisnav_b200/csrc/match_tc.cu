@@ -139,31 +139,32 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(MT_BM, MT_BN);
-            bool ok = tc::mbar_wait(a_full, 0, err, 102);
-            for (int j = 0; ok && j < n_tiles; ++j) {
-                const int s = j % MT_STAGES;
-                const uint32_t ph = (j / MT_STAGES) & 1;
-                if (!tc::mbar_wait(&b_full[s], ph, err, 103)) break;
-                if (j >= MT_STAGES && !tc::mbar_wait(&t_empty[s], ph ^ 1, err, 104)) break;
-                tc::tc_fence_after();
+        // ===== MMA issuer: warp converged, one elected lane issues =====
+        const uint32_t idesc = tc::make_idesc_bf16(MT_BM, MT_BN);
+        bool ok = tc::mbar_wait(a_full, 0, err, 102);
+        const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA), 1024);
+        const uint64_t db00 = tc::make_smem_desc_sw128(tc::smem_u32(sB), 1024);
+        for (int j = 0; ok && j < n_tiles; ++j) {
+            const int s = j % MT_STAGES;
+            const uint32_t ph = (j / MT_STAGES) & 1;
+            if (!tc::mbar_wait(&b_full[s], ph, err, 103)) break;
+            if (j >= MT_STAGES && !tc::mbar_wait(&t_empty[s], ph ^ 1, err, 104)) break;
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(s * MT_BN);
+                const uint64_t db0 = db00 + (uint64_t)((s * MT_TILE_BYTES) >> 4);
 #pragma unroll
                 for (int c = 0; c < MT_K / MT_KC; ++c) {
-                    const uint32_t a_addr = tc::smem_u32(sA + c * MT_CHUNK_BYTES);
-                    const uint32_t b_addr = tc::smem_u32(sB + s * MT_TILE_BYTES + c * MT_CHUNK_BYTES);
 #pragma unroll
                     for (int k = 0; k < MT_KC / 16; ++k) {
-                        const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 1024);
-                        const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 1024);
-                        tc::umma_bf16(d_tmem, da, db, idesc, (c | k) ? 1u : 0u);
+                        const uint64_t off = (uint64_t)((c * MT_CHUNK_BYTES + k * 32) >> 4);
+                        tc::umma_bf16(d_tmem, da0 + off, db0 + off, idesc, (c | k) ? 1u : 0u);
                     }
                 }
                 tc::umma_commit(&b_empty[s]);  // smem stage reusable once these MMAs have read it
                 tc::umma_commit(&t_full[s]);   // accumulator ready for the epilogue
             }
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread <-> TMEM lane <-> row =====
