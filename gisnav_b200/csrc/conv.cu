@@ -65,41 +65,53 @@ void gnb_conv_free(gnb_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1a: u8 image -> 64 channels, 3x3, ReLU, bf16 NHWC.  Cin = 1, so this is 9 FMAs per output:
-// HBM-bound (1 B in, 128 B out per pixel).  One thread per pixel, 16-byte stores.
+// conv1a: u8 image -> 64 channels, 3x3, ReLU, bf16 NHWC.  Cin = 1, so this is 9 FMAs per output and
+// the kernel is HBM-write-bound (1 B in, 128 B out per pixel).  CTA = 8 x 32 pixel tile; lane l of a
+// warp owns channels [8 (l%8), +8) of pixel (l/8) of a 4-pixel group, so every warp-wide 16-byte
+// store covers 512 contiguous bytes.  The 72 weights a thread needs live in registers.
+#define C1_TH 8
+#define C1_TW 32
 __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__ img, const bf16* __restrict__ wt,
                                                      const float* __restrict__ bias, int h, int w, bf16* __restrict__ out) {
-    __shared__ float wsm[9][64];
-    __shared__ float bsm[64];
-    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) wsm[i / 64][i % 64] = __bfloat162float(wt[i]);
-    if (threadIdx.x < 64) bsm[threadIdx.x] = bias[threadIdx.x];
-    __syncthreads();
-    const int b = blockIdx.z;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= w || y >= h) return;
+    __shared__ float patch[C1_TH + 2][C1_TW + 2 + 2];
+    const int b = blockIdx.z, y0 = blockIdx.y * C1_TH, x0 = blockIdx.x * C1_TW;
     const uint8_t* im = img + (size_t)b * h * w;
-    float v[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    for (int i = threadIdx.x; i < (C1_TH + 2) * (C1_TW + 2); i += 256) {
+        const int ly = i / (C1_TW + 2), lx = i % (C1_TW + 2);
+        const int y = y0 + ly - 1, x = x0 + lx - 1;
         float f = 0.f;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) f = (float)im[(size_t)yy * w + xx] / 255.0f;
-        v[t] = __bfloat162float(__float2bfloat16_rn(f));
+        if (y >= 0 && y < h && x >= 0 && x < w) f = (float)im[(size_t)y * w + x] / 255.0f;
+        patch[ly][lx] = __bfloat162float(__float2bfloat16_rn(f));
     }
-    bf16* o = out + ((size_t)b * h * w + (size_t)y * w + x) * 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = (lane & 7) * 8, sub = lane >> 3;
+    float wr[9][8], br[8];
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 8) {
-        __align__(16) bf16 r[8];
+    for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float acc = 0.f;
+        for (int j = 0; j < 8; ++j) wr[t][j] = __bfloat162float(wt[t * 64 + c0 + j]);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wsm[t][c0 + j], acc);
-            acc += bsm[c0 + j];
-            r[j] = __float2bfloat16_rn(fmaxf(acc, 0.f));
+    for (int j = 0; j < 8; ++j) br[j] = bias[c0 + j];
+    __syncthreads();
+    // warp `warp` owns row y0 + warp; 8 iterations of 4 pixels
+    const int ly = warp, y = y0 + ly;
+    if (y >= h) return;
+#pragma unroll 2
+    for (int it = 0; it < C1_TW / 4; ++it) {
+        const int lx = it * 4 + sub, x = x0 + lx;
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = patch[ly + t / 3][lx + t % 3];
+        __align__(16) __nv_bfloat162 r[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { a0 = fmaf(v[t], wr[t][j], a0); a1 = fmaf(v[t], wr[t][j + 1], a1); }
+            a0 += br[j]; a1 += br[j + 1];
+            r[j / 2] = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
         }
-        *reinterpret_cast<uint4*>(o + c0) = *reinterpret_cast<const uint4*>(r);
+        if (x < w) *reinterpret_cast<uint4*>(out + ((size_t)b * h * w + (size_t)y * w + x) * 64 + c0) = *reinterpret_cast<const uint4*>(r);
     }
 }
 
@@ -272,7 +284,7 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w) {
     cw.n = n; cw.h = h; cw.w = w;
     int rc;
     {
-        dim3 grid(ceil_div(w, 32), ceil_div(h, 8), n);
+        dim3 grid(ceil_div(w, C1_TW), ceil_div(h, C1_TH), n);
         GNB_KERNEL(ctx, "conv1a_kernel", conv1a_kernel<<<grid, 256, 0, ctx->stream>>>(cw.img, ctx->layers[L1A].w, ctx->layers[L1A].bias, h, w, cw.a1a));
     }
     if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;

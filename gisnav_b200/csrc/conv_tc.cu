@@ -19,7 +19,7 @@
 
 int* gnb_tc_err_dev(gnb_ctx* ctx);
 
-struct ConvTcLayerMaps { CUtensorMap w; int valid; };
+struct ConvTcLayerMaps { CUtensorMap w; CUtensorMap w64; CUtensorMap w128; int valid; };
 static ConvTcLayerMaps g_wmaps[GNB_NUM_LAYERS];
 
 template <int NPAD>
@@ -176,13 +176,17 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const __grid_constant__ CU
 #define H2_HALO_BYTES (H2_HH * H2_HW * 128)           // 23040
 #define H2_HALO_STRIDE ((H2_HALO_BYTES + 1023) / 1024 * 1024)
 
-template <int NPAD, int STAGES>
+// KCH = Cin / 64 (1 or 2).  With KCH = 2 the A ring holds one (tile, 64-channel chunk) halo box per
+// stage and the output channels are split into `n_slices` slices of NPAD channels: a CTA keeps the
+// weights of ONE slice resident for the whole layer (blockIdx.x % n_slices) and loops over tiles,
+// so the only streamed operand is the 22.5 KB halo box (L2 traffic per tile = n_slices x KCH x 22.5 KB).
+template <int NPAD, int KCH, int STAGES>
 __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_in,
                                                               const __grid_constant__ CUtensorMap tmap_w,
                                                               const float* __restrict__ bias, int h, int w, int n_img, int cout,
-                                                              bf16* __restrict__ out_bf, int relu, int pool, int* err) {
-    constexpr int W_TAP_BYTES = NPAD * 128;
-    constexpr int W_BYTES = 9 * W_TAP_BYTES;
+                                                              int n_slices, bf16* __restrict__ out_bf, int relu, int pool, int* err) {
+    constexpr int W_TAP_BYTES = NPAD * 128;        // one (tap, chunk) block
+    constexpr int W_BYTES = 9 * KCH * W_TAP_BYTES;
     constexpr int TMEM_COLS = 2 * NPAD;  // 128 or 256
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -201,6 +205,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     const int tiles_x = (w + H2_TW - 1) / H2_TW, tiles_y = (h + H2_TH - 1) / H2_TH;
     const int tiles_per_img = tiles_x * tiles_y;
     const int total = tiles_per_img * n_img;
+    const int slice = blockIdx.x % n_slices;           // output-channel slice this CTA owns
+    const int tile0 = blockIdx.x / n_slices;           // first tile, then stride = CTAs per slice
+    const int tstride = gridDim.x / n_slices;
+    const int ch0 = slice * NPAD;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_in);
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
         tc::tmem_alloc(tmem_slot, TMEM_COLS);
         tc::tmem_relinquish();
     }
-    if (threadIdx.x >= 128 && threadIdx.x - 128 < NPAD) s_bias[threadIdx.x - 128] = bias[threadIdx.x - 128];
+    if (threadIdx.x >= 128 && threadIdx.x - 128 < NPAD) s_bias[threadIdx.x - 128] = bias[ch0 + threadIdx.x - 128];
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -223,16 +231,22 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     if (warp == 0) {
         if (lane == 0) {
             tc::mbar_arrive_expect_tx(w_full, W_BYTES);
-            for (int t = 0; t < 9; ++t) tc::tma_load_3d(sW + t * W_TAP_BYTES, &tmap_w, w_full, 0, 0, t);
-            int i = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                if (i >= STAGES && !tc::mbar_wait(&a_empty[s], ph ^ 1, err, 211)) break;
+            for (int t = 0; t < 9; ++t)
+                for (int c = 0; c < KCH; ++c)
+                    tc::tma_load_3d(sW + (t * KCH + c) * W_TAP_BYTES, &tmap_w, w_full, c * 64, ch0, t);
+            int i = 0;  // ring index over (tile, chunk) boxes
+            for (int tile = tile0; tile < total; tile += tstride) {
                 const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int y0 = (rem / tiles_x) * H2_TH, x0 = (rem % tiles_x) * H2_TW;
-                tc::mbar_arrive_expect_tx(&a_full[s], H2_HALO_BYTES);
-                tc::tma_load_4d(sA + s * H2_HALO_STRIDE, &tmap_in, &a_full[s], 0, x0 - 1, y0 - 1, img);
+                bool ok = true;
+                for (int c = 0; c < KCH; ++c, ++i) {
+                    const int s = i % STAGES;
+                    const uint32_t ph = (i / STAGES) & 1;
+                    if (i >= STAGES && !tc::mbar_wait(&a_empty[s], ph ^ 1, err, 211)) { ok = false; break; }
+                    tc::mbar_arrive_expect_tx(&a_full[s], H2_HALO_BYTES);
+                    tc::tma_load_4d(sA + s * H2_HALO_STRIDE, &tmap_in, &a_full[s], c * 64, x0 - 1, y0 - 1, img);
+                }
+                if (!ok) break;
             }
         }
     } else if (warp == 1) {
@@ -241,34 +255,38 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
         const uint32_t idesc = tc::make_idesc_bf16(128, NPAD);
         bool ok = tc::mbar_wait(w_full, 0, err, 212);
         const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
-        int i = 0;
-        for (int tile = blockIdx.x; ok && tile < total; tile += gridDim.x, ++i) {
-            const int s = i % STAGES, as = i & 1;
-            if (!tc::mbar_wait(&a_full[s], (i / STAGES) & 1, err, 213)) break;
-            if (i >= 2 && !tc::mbar_wait(&t_empty[as], ((i >> 1) & 1) ^ 1, err, 214)) break;
-            tc::tc_fence_after();
-            const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
+        int i = 0, ti = 0;
+        for (int tile = tile0; ok && tile < total; tile += tstride, ++ti) {
+            const int as = ti & 1;
+            if (ti >= 2 && !tc::mbar_wait(&t_empty[as], ((ti >> 1) & 1) ^ 1, err, 214)) break;
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * NPAD);
-            if (tc::elect_one()) {
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
+            for (int c = 0; c < KCH; ++c, ++i) {
+                const int s = i % STAGES;
+                if (!tc::mbar_wait(&a_full[s], (i / STAGES) & 1, err, 213)) { ok = false; break; }
+                tc::tc_fence_after();
+                const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
+                if (tc::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
-                        const uint64_t db = db0 + (uint64_t)((t * W_TAP_BYTES + k * 32) >> 4);
-                        tc::umma_bf16(d_tmem, da, db, idesc, (t | k) ? 1u : 0u);
+                    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
+                            const uint64_t db = db0 + (uint64_t)(((t * KCH + c) * W_TAP_BYTES + k * 32) >> 4);
+                            tc::umma_bf16(d_tmem, da, db, idesc, (c | t | k) ? 1u : 0u);
+                        }
                     }
+                    tc::umma_commit(&a_empty[s]);
+                    if (c == KCH - 1) tc::umma_commit(&t_full[as]);
                 }
-                tc::umma_commit(&a_empty[s]);
-                tc::umma_commit(&t_full[as]);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int yl = 4 * q + (lane >> 3), xl = lane & 7;
         int i = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+        for (int tile = tile0; tile < total; tile += tstride, ++i) {
             const int as = i & 1;
             const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
             const int y = (rem / tiles_x) * H2_TH + yl, x = (rem % tiles_x) * H2_TW + xl;
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
                     packed[j] = u;
                 }
                 if (writer) {
-                    uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + c0);
+                    uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + ch0 + c0);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
                 }
@@ -328,19 +346,23 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     }
 }
 
-template <int NPAD, int STAGES>
+template <int NPAD, int KCH, int STAGES>
 static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
                                bf16* out_bf, int relu, int pool, const char* name) {
-    constexpr int smem = 1024 + 9 * NPAD * 128 + STAGES * H2_HALO_STRIDE + 256 + NPAD * 4;
+    constexpr int smem = 1024 + 9 * KCH * NPAD * 128 + STAGES * H2_HALO_STRIDE + 256 + NPAD * 4;
     static bool attr_set = false;
     if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_kernel<NPAD, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_kernel<NPAD, KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
+    const int n_slices = L.cout_pad / NPAD;
     const int total = ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n;
-    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-    GNB_KERNEL(ctx, name, conv_tc_halo_kernel<NPAD, STAGES><<<grid, 256, smem, ctx->stream>>>(
-        tin, tw, L.bias, h, w, n, L.cout, out_bf, relu, pool, gnb_tc_err_dev(ctx)));
+    int per_slice = ctx->sm_count / n_slices;
+    if (per_slice > total) per_slice = total;
+    if (per_slice < 1) per_slice = 1;
+    const int grid = per_slice * n_slices;
+    GNB_KERNEL(ctx, name, conv_tc_halo_kernel<NPAD, KCH, STAGES><<<grid, 256, smem, ctx->stream>>>(
+        tin, tw, L.bias, h, w, n, L.cout, n_slices, out_bf, relu, pool, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
 
@@ -370,6 +392,12 @@ int gnb_conv_tc_init(gnb_ctx* ctx) {
         const uint32_t box[3] = {64, (uint32_t)L.cout_pad, 1};
         int rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].w, L.w, 3, dims, strides, box);
         if (rc) return rc;
+        const uint32_t box64[3] = {64, 64, 1};
+        if ((rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].w64, L.w, 3, dims, strides, box64))) return rc;
+        if (L.cout_pad >= 128) {
+            const uint32_t box128[3] = {64, 128, 1};
+            if ((rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].w128, L.w, 3, dims, strides, box128))) return rc;
+        }
         g_wmaps[l].valid = 1;
     }
     return GNB_OK;
@@ -387,11 +415,15 @@ int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, i
     const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)L.cin * 2, (uint64_t)w * L.cin * 2, (uint64_t)h * w * L.cin * 2};
     int rc;
-    if (!v1_only && L.cin == 64 && L.ks == 3 && out_bf && (L.cout_pad == 64 || L.cout_pad == 128)) {
+    if (!v1_only && L.ks == 3 && out_bf && (L.cin == 64 || L.cin == 128) && (L.cout_pad % 64) == 0) {
         const uint32_t hbox[4] = {64, H2_HW, H2_HH, 1};
         if ((rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(in), 4, dims, strides, hbox))) return rc;
-        if (L.cout_pad == 64) return launch_conv_tc_halo<64, 4>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, relu, pool, kNames[lid]);
-        return launch_conv_tc_halo<128, 3>(ctx, tin, g_wmaps[lid].w, L, n, h, w, out_bf, relu, pool, kNames[lid]);
+        if (L.cin == 64 && L.cout_pad == 64)
+            return launch_conv_tc_halo<64, 1, 4>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
+        if (L.cin == 64 && L.cout_pad == 128)
+            return launch_conv_tc_halo<128, 1, 3>(ctx, tin, g_wmaps[lid].w128, L, n, h, w, out_bf, relu, pool, kNames[lid]);
+        if (L.cin == 128)  // 128 -> 128 / 256: slices of 64 output channels, weights of a slice resident (144 KB)
+            return launch_conv_tc_halo<64, 2, 3>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
     }
     const uint32_t box[4] = {64, CT_TW, CT_TH, 1};
     rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(in), 4, dims, strides, box);
