@@ -295,9 +295,9 @@ extern "C" int gnb_extract(gnb_ctx* ctx, const uint8_t* image, int h, int w, int
     if ((rc = check_image(ctx, h, w))) return rc;
     if (stride < w) { GNB_SET_ERR(ctx, "stride < width"); return GNB_E_INVALID; }
     GNB_CUDA(ctx, cudaMemcpy2DAsync(ctx->cw.img, w, image, stride, w, h, kind_in(on_device), ctx->stream));
-    if ((rc = gnb_conv_forward(ctx, 1, h, w))) return rc;
+    if ((rc = gnb_conv_forward(ctx, 1, h, w, 0))) return rc;
     if ((rc = gnb_kp_select(ctx, ctx->cw.score, 1, h, w, 0))) return rc;
-    if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, 1, h, w, 0))) return rc;
+    if ((rc = gnb_describe(ctx, 1, h, w, 0))) return rc;
     int n = 0;
     if ((rc = read_count(ctx, ctx->kp_count, &n))) return rc;
     if (n < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); return GNB_E_CAPACITY; }
@@ -426,14 +426,14 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
     if (dems) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dems, (size_t)batch * ht * wt, kin, ctx->stream));
     // query frames -> slots [0, batch)
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.img, frames, (size_t)batch * hq * wq, kin, ctx->stream));
-    if ((rc = gnb_conv_forward(ctx, batch, hq, wq))) return rc;
+    if ((rc = gnb_conv_forward(ctx, batch, hq, wq, 0))) return rc;
     if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, hq, wq, 0))) return rc;
-    if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, batch, hq, wq, 0))) return rc;
+    if ((rc = gnb_describe(ctx, batch, hq, wq, 0))) return rc;
     // reference rasters -> slots [max_batch, max_batch + batch)
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.img, tiles, (size_t)batch * ht * wt, kin, ctx->stream));
-    if ((rc = gnb_conv_forward(ctx, batch, ht, wt))) return rc;
+    if ((rc = gnb_conv_forward(ctx, batch, ht, wt, 0))) return rc;
     if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, ht, wt, sb))) return rc;
-    if ((rc = gnb_kp_sample(ctx, ctx->cw.dense, batch, ht, wt, sb))) return rc;
+    if ((rc = gnb_describe(ctx, batch, ht, wt, sb))) return rc;
     if ((rc = gnb_match_project(ctx, 0, batch))) return rc;
     if ((rc = gnb_match_project(ctx, sb, batch))) return rc;
     if ((rc = gnb_match_pairs(ctx, batch, 0, sb))) return rc;
@@ -459,7 +459,7 @@ extern "C" int gnb_dense(gnb_ctx* ctx, const uint8_t* image, int h, int w, int s
     int rc;
     if ((rc = check_image(ctx, h, w))) return rc;
     GNB_CUDA(ctx, cudaMemcpy2DAsync(ctx->cw.img, w, image, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = gnb_conv_forward(ctx, 1, h, w))) return rc;
+    if ((rc = gnb_conv_forward(ctx, 1, h, w, 1))) return rc;
     if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->cw.score, sizeof(float) * h * w, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_dense) GNB_CUDA(ctx, cudaMemcpyAsync(out_dense, ctx->cw.dense, sizeof(float) * (h / 8) * (w / 8) * 256, cudaMemcpyDeviceToHost, ctx->stream));
     GNB_SYNC(ctx);

@@ -143,7 +143,9 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int gnb_conv_init(gnb_ctx* ctx, const float* blob_floats);  // repack weights
 void gnb_conv_free(gnb_ctx* ctx);
 // run the dense stack on cw.img (n images of h x w already resident)
-int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w);
+int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc);
+// descriptors of the selected keypoints of `n` images (slots slot0..): on-demand tcgen05 head or dense+sample
+int gnb_describe(gnb_ctx* ctx, int n, int h, int w, int slot0);
 // tcgen05 implicit-GEMM conv (conv_tc.cu); returns GNB_E_INVALID if a layer shape is unsupported
 int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, int h, int w, bf16* out_bf,
                       float* out_f, int relu, int pool);

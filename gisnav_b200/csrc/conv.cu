@@ -11,6 +11,11 @@
 
 #include <vector>
 
+struct CUtensorMap_st;
+const CUtensorMap_st* gnb_conv_tc_wmap(int lid);
+int gnb_score_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* apa, const float* bias, int n, int hc, int wc, float* score);
+int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0);
+
 // ------------------------------------------------------------------------------------------------
 // host-side bf16 rounding (round to nearest even), identical to torch's .to(bfloat16)
 static inline uint16_t f32_to_bf16_bits(float f) {
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(256) l2norm256_kernel(float* __restrict__ d, i
 }
 
 // ------------------------------------------------------------------------------------------------
-int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w) {
+int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
     ConvWorkspace& cw = ctx->cw;
     if (n > cw.cap_images || (size_t)h * w > cw.cap_pixels || (h % 8) || (w % 8)) {
         GNB_SET_ERR(ctx, "conv_forward: %d images of %dx%d exceed the workspace or are not multiples of 8", n, h, w);
@@ -295,11 +300,25 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w) {
     if ((rc = conv_layer(ctx, L4A, cw.p3, n, h / 8, w / 8, cw.a4a, nullptr, 1, 0))) return rc;
     if ((rc = conv_layer(ctx, L4B, cw.a4a, n, h / 8, w / 8, cw.a4b, nullptr, 1, 0))) return rc;
     if ((rc = conv_layer(ctx, LPA, cw.a4b, n, h / 8, w / 8, cw.apa, nullptr, 1, 0))) return rc;
-    if ((rc = conv_layer(ctx, LPB, cw.apa, n, h / 8, w / 8, nullptr, cw.semi, 0, 0))) return rc;
-    if ((rc = conv_layer(ctx, LDA, cw.a4b, n, h / 8, w / 8, cw.ada, nullptr, 1, 0))) return rc;
-    if ((rc = conv_layer(ctx, LDB, cw.ada, n, h / 8, w / 8, nullptr, cw.dense, 0, 0))) return rc;
     const int cells = n * (h / 8) * (w / 8);
-    GNB_KERNEL(ctx, "softmax_d2s_kernel", softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score));
-    GNB_KERNEL(ctx, "l2norm256_kernel", l2norm256_kernel<<<ceil_div(cells * 32, 256), 256, 0, ctx->stream>>>(cw.dense, cells));
+    if (ctx->cfg.conv_impl == 0) {
+        // detector head fused: 1x1 conv + softmax + depth-to-space straight into the score map
+        if ((rc = gnb_score_head_tc(ctx, gnb_conv_tc_wmap(LPB), cw.apa, ctx->layers[LPB].bias, n, h / 8, w / 8, cw.score))) return rc;
+    } else {
+        if ((rc = conv_layer(ctx, LPB, cw.apa, n, h / 8, w / 8, nullptr, cw.semi, 0, 0))) return rc;
+        GNB_KERNEL(ctx, "softmax_d2s_kernel", softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score));
+    }
+    if ((rc = conv_layer(ctx, LDA, cw.a4b, n, h / 8, w / 8, cw.ada, nullptr, 1, 0))) return rc;
+    if (dense_desc || ctx->cfg.conv_impl != 0) {
+        // dense 256-channel map (validation / stage hooks); the product path evaluates convDb on demand
+        if ((rc = conv_layer(ctx, LDB, cw.ada, n, h / 8, w / 8, nullptr, cw.dense, 0, 0))) return rc;
+        GNB_KERNEL(ctx, "l2norm256_kernel", l2norm256_kernel<<<ceil_div(cells * 32, 256), 256, 0, ctx->stream>>>(cw.dense, cells));
+    }
     return GNB_OK;
+}
+
+int gnb_describe(gnb_ctx* ctx, int n, int h, int w, int slot0) {
+    if (ctx->cfg.conv_impl == 0)
+        return gnb_desc_head_tc(ctx, gnb_conv_tc_wmap(LDB), ctx->cw.ada, ctx->layers[LDB].bias, n, h, w, slot0);
+    return gnb_kp_sample(ctx, ctx->cw.dense, n, h, w, slot0);
 }

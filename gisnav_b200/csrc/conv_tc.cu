@@ -381,6 +381,8 @@ static int launch_conv_tc(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMa
     return GNB_OK;
 }
 
+const CUtensorMap* gnb_conv_tc_wmap(int lid) { return g_wmaps[lid].valid ? &g_wmaps[lid].w : nullptr; }
+
 int gnb_conv_tc_init(gnb_ctx* ctx) {
     if (!gnb_tc_err_dev(ctx)) { GNB_SET_ERR(ctx, "cannot allocate the host-mapped error word"); return GNB_E_CUDA; }
     for (int l = 0; l < GNB_NUM_LAYERS; ++l) {

@@ -658,8 +658,11 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(
                     for (int r = 0; r < 6; ++r) g[r] = tot[21 + r];
                     cost = c2;
                     lambda *= 0.1; if (lambda < 1e-12) lambda = 1e-12;
-                    if (rel < 1e-15 || step < 1e-13) s_state = 1;
+                    if (rel < 1e-12 || step < 1e-10) s_state = 1;
                 } else {
+                    const double step = sqrt(dxs[0] * dxs[0] + dxs[1] * dxs[1] + dxs[2] * dxs[2] + dxs[3] * dxs[3] +
+                                             dxs[4] * dxs[4] + dxs[5] * dxs[5]);
+                    if (step < 1e-9) s_state = 1;  // no measurable improvement left
                     lambda *= 10.0;
                     if (lambda > 1e12) s_state = 1;
                 }

@@ -436,8 +436,10 @@ static void lm_refit(const float *obj, const float *img, const uint8_t *mask, ui
             *p = q;
             cost = lm_accumulate(obj, img, mask, n, k, p, H, g);
             lambda *= 0.1; if (lambda < 1e-12) lambda = 1e-12;
-            if (rel < 1e-15 || step < 1e-13) break;
+            if (rel < 1e-12 || step < 1e-10) break;
         } else {
+            double step = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2] + dx[3] * dx[3] + dx[4] * dx[4] + dx[5] * dx[5]);
+            if (step < 1e-9) break; /* no measurable improvement left */
             lambda *= 10.0;
             if (lambda > 1e12) break;
         }

@@ -125,6 +125,29 @@ def test_k3_sampling_matches_oracle(rand_blob, stages, oracle):
     ctx.close()
 
 
+def test_k3_on_demand_descriptor_head_matches_oracle(rand_blob, rand_params, oracle):
+    """Product path: convDb is evaluated only at the 4 cells around each keypoint (tcgen05, fused with
+    normalise + bilinear + normalise).  Compare with the oracle's dense map sampled at the SAME keypoints."""
+    img = np.ascontiguousarray(synth.ground_texture(512, seed=12, n_shapes=300)[10:130, 20:220])  # 120 x 200
+    ctx = _ctx(rand_blob, conv_impl=0, max_keypoints=300)
+    xy, sc, desc = KeypointExtractor(ctx).detect_and_compute_arrays(img)
+    assert len(xy) > 50
+    _, dense = oracle.superpoint_ref.forward_dense(img, rand_params)
+    ref = oracle.sample_ref.sample_descriptors(dense, xy, img.shape)
+    np.testing.assert_allclose(np.linalg.norm(desc, axis=1), 1.0, atol=1e-5)
+    assert np.abs(desc - ref).max() <= 0.02  # bf16 activation noise upstream, as in the dense test
+    assert np.mean(np.abs(desc - ref)) <= 0.002
+    # the validation path (dense map + sampling kernel) agrees with the on-demand head on the same keypoints
+    ctx2 = _ctx(rand_blob, conv_impl=1, max_keypoints=300)
+    xy2, _, desc2 = KeypointExtractor(ctx2).detect_and_compute_arrays(img)
+    common = {tuple(p): i for i, p in enumerate(xy2)}
+    pairs = [(i, common[tuple(p)]) for i, p in enumerate(xy) if tuple(p) in common]
+    assert len(pairs) > 0.8 * len(xy)
+    d = np.abs(desc[[a for a, _ in pairs]] - desc2[[b for _, b in pairs]])
+    assert d.max() <= 0.02
+    ctx.close(); ctx2.close()
+
+
 # ---- K4: matcher ------------------------------------------------------------------------------------
 def _desc_sets(rng, n, m, shared, noise=0.05):
     a = rng.standard_normal((n, 256)).astype(np.float32)
