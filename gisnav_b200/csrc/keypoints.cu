@@ -127,15 +127,16 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
 #define N4_REG 104
 #define N4_PITCH 105
 #define N4_RUN 13
-#define N4_THREADS 512
+#define N4_THREADS 416  // 2 items per thread per pass: 104 lines x 8 runs = 832
 
 template <bool ROWS, typename Src, typename Sink>
 __device__ __forceinline__ void n4_pass(Src src, Sink sink) {
     const float NEG = -INFINITY;
     for (int item = threadIdx.x; item < N4_REG * (N4_REG / N4_RUN); item += N4_THREADS) {
         int line, run;
-        if (ROWS) { line = item / (N4_REG / N4_RUN); run = item % (N4_REG / N4_RUN); }  // adjacent lanes: same row
-        else { line = item % N4_REG; run = item / N4_REG; }                            // adjacent lanes: adjacent columns
+        // adjacent lanes own adjacent lines: row pass -> addresses PITCH (odd) apart, column pass ->
+        // consecutive addresses; both are bank-conflict free
+        line = item % N4_REG; run = item / N4_REG;
         const int p0 = run * N4_RUN - 4;
         float v[N4_RUN + 8];
 #pragma unroll
