@@ -9,11 +9,13 @@
 // path for the Cin>=64 layers is the tcgen05 implicit GEMM in conv_tc.cu.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 struct CUtensorMap_st;
 const CUtensorMap_st* gnb_conv_tc_wmap(int lid);
 int gnb_score_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* apa, const float* bias, int n, int hc, int wc, float* score);
+int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out_p1);
 int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0);
 
 // ------------------------------------------------------------------------------------------------
@@ -288,11 +290,18 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
     }
     cw.n = n; cw.h = h; cw.w = w;
     int rc;
-    {
+    static const int no_fuse = getenv("GNB_NO_CONV1_FUSION") ? atoi(getenv("GNB_NO_CONV1_FUSION")) : 0;
+    const bool fused1 = ctx->cfg.conv_impl == 0 && !no_fuse;
+    if (!fused1 || dense_desc) {
+        // standalone conv1a: SIMT path, or the stage hooks that expose the conv1a activation
         dim3 grid(ceil_div(w, C1_TW), ceil_div(h, C1_TH), n);
         GNB_KERNEL(ctx, "conv1a_kernel", conv1a_kernel<<<grid, 256, 0, ctx->stream>>>(cw.img, ctx->layers[L1A].w, ctx->layers[L1A].bias, h, w, cw.a1a));
     }
-    if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
+    if (fused1) {
+        if ((rc = gnb_conv1_fused_tc(ctx, cw.img, n, h, w, cw.p1))) return rc;
+    } else {
+        if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
+    }
     if ((rc = conv_layer(ctx, L2A, cw.p1, n, h / 2, w / 2, cw.a2a, nullptr, 1, 0))) return rc;
     if ((rc = conv_layer(ctx, L2B, cw.a2a, n, h / 2, w / 2, cw.p2, nullptr, 1, 1))) return rc;
     if ((rc = conv_layer(ctx, L3A, cw.p2, n, h / 4, w / 4, cw.a3a, nullptr, 1, 0))) return rc;

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     uint64_t* t_full = a_empty + STAGES;     // [2]
     uint64_t* t_empty = t_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // [NPAD]
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [NPAD], 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (w + H2_TW - 1) / H2_TW, tiles_y = (h + H2_TH - 1) / H2_TH;
@@ -310,22 +310,24 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
                 tc::tmem_ld_wait();
                 uint32_t packed[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a0 = __uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j];
-                    float a1 = __uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1];
-                    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                    __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
-                    uint32_t u = *reinterpret_cast<uint32_t*>(&pk);
-                    if (pool) {  // max of bf16-rounded values == rounding of the max (monotone)
-                        __nv_bfloat162 o = pk;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j4]);
+                    const float a0 = __uint_as_float(v[4 * j4]) + bb.x, a1 = __uint_as_float(v[4 * j4 + 1]) + bb.y;
+                    const float a2 = __uint_as_float(v[4 * j4 + 2]) + bb.z, a3 = __uint_as_float(v[4 * j4 + 3]) + bb.w;
+                    packed[2 * j4] = relu ? tc::pack_bf16x2_relu(a0, a1) : tc::pack_bf16x2(a0, a1);
+                    packed[2 * j4 + 1] = relu ? tc::pack_bf16x2_relu(a2, a3) : tc::pack_bf16x2(a2, a3);
+                }
+                if (pool) {  // max of bf16-rounded values == rounding of the max (monotone)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t u = packed[j];
                         uint32_t u1 = __shfl_xor_sync(0xffffffffu, u, 1);
-                        o = __hmax2(o, *reinterpret_cast<__nv_bfloat162*>(&u1));
+                        __nv_bfloat162 o = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u), *reinterpret_cast<__nv_bfloat162*>(&u1));
                         u = *reinterpret_cast<uint32_t*>(&o);
                         uint32_t u8 = __shfl_xor_sync(0xffffffffu, u, 8);
                         o = __hmax2(o, *reinterpret_cast<__nv_bfloat162*>(&u8));
-                        u = *reinterpret_cast<uint32_t*>(&o);
+                        packed[j] = *reinterpret_cast<uint32_t*>(&o);
                     }
-                    packed[j] = u;
                 }
                 if (writer) {
                     uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + ch0 + c0);
@@ -363,6 +365,293 @@ static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUten
     const int grid = per_slice * n_slices;
     GNB_KERNEL(ctx, name, conv_tc_halo_kernel<NPAD, KCH, STAGES><<<grid, 256, smem, ctx->stream>>>(
         tin, tw, L.bias, h, w, n, L.cout, n_slices, out_bf, relu, pool, gnb_tc_err_dev(ctx)));
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1a + conv1b + 2x2 max-pool in ONE kernel.  The 64-channel full-resolution activation
+// (128 B/pixel written and read back = 2/3 of the whole stack's HBM traffic) never leaves the SM:
+//   im2col warps : 3x3 neighbourhood of the u8 image -> bf16 [256 halo rows x K=16] operand (9 taps)
+//   MMA1         : conv1a as two tcgen05.mma (M=128, N=64, K=16) -> TMEM T1 (fp32)
+//   convert warps: T1 + bias, ReLU, bf16 -> the 18x10x64ch halo tile of conv1b, written directly in
+//                  the 128B-swizzle layout (zero outside the image = conv1b's padding)
+//   MMA2         : conv1b, 36 tcgen05.mma over nine shifted descriptor views (as conv_tc_halo_kernel)
+//   epilogue     : bias, ReLU, 2x2 max-pool, bf16 store at half resolution
+// All five stages are double-buffered and run concurrently on different tiles.
+#define F1_A1_BYTES (256 * 128)      // 256 rows x 128 B (only the first 32 B = K 16 of a row are used)
+#define F1_W1A_BYTES (64 * 128)
+#define F1_W1B_BYTES (9 * 64 * 128)
+#define F1_THREADS 512               // 16 warps: 0 W-loader, 1 MMA, 2 TMEM alloc, 4-7 epilogue, 8-11 convert, 12-15 im2col
+#define F1_SMEM (1024 + F1_W1B_BYTES + F1_W1A_BYTES + 2 * F1_A1_BYTES + 2 * H2_HALO_STRIDE + 512 + 2 * 64 * 4)
+
+__global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_t* __restrict__ img, const bf16* __restrict__ w1a,
+                                                                    const float* __restrict__ bias1a,
+                                                                    const __grid_constant__ CUtensorMap tmap_w1b,
+                                                                    const float* __restrict__ bias1b, int h, int w, int n_img,
+                                                                    bf16* __restrict__ out_bf, int* err) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW1b = smem;
+    uint8_t* sW1a = sW1b + F1_W1B_BYTES;
+    uint8_t* sA1 = sW1a + F1_W1A_BYTES;                 // [2][256 x 128 B]
+    uint8_t* sA2 = sA1 + 2 * F1_A1_BYTES;               // [2][halo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA2 + 2 * H2_HALO_STRIDE);
+    uint64_t* w_full = bars;          // 1
+    uint64_t* a1_full = bars + 1;     // [2] im2col -> MMA1      (4 arrivals: one per im2col warp)
+    uint64_t* a1_empty = bars + 3;    // [2] MMA1 done reading A1 (tcgen05.commit)
+    uint64_t* t1_full = bars + 5;     // [2] MMA1 -> convert      (tcgen05.commit)
+    uint64_t* t1_empty = bars + 7;    // [2] convert -> MMA1      (4 arrivals)
+    uint64_t* a2_full = bars + 9;     // [2] convert -> MMA2      (4 arrivals)
+    uint64_t* a2_empty = bars + 11;   // [2] MMA2 done reading A2 (tcgen05.commit)
+    uint64_t* t2_full = bars + 13;    // [2] MMA2 -> epilogue     (tcgen05.commit)
+    uint64_t* t2_empty = bars + 15;   // [2] epilogue -> MMA2     (4 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    float* s_b1a = reinterpret_cast<float*>(tmem_slot + 4);
+    float* s_b1b = s_b1a + 64;
+    __shared__ unsigned short s_lut[256];   // u8 -> bf16(v / 255)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (w + H2_TW - 1) / H2_TW, tiles_y = (h + H2_TH - 1) / H2_TH;
+    const int tiles_per_img = tiles_x * tiles_y;
+    const int total = tiles_per_img * n_img;
+    if (threadIdx.x >= 256) {
+        const __nv_bfloat16 q = __float2bfloat16_rn((float)(threadIdx.x - 256) / 255.0f);
+        s_lut[threadIdx.x - 256] = *reinterpret_cast<const unsigned short*>(&q);
+    }
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_w1b);
+        tc::mbar_init(w_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&a1_full[s], 4); tc::mbar_init(&a1_empty[s], 1);
+            tc::mbar_init(&t1_full[s], 1); tc::mbar_init(&t1_empty[s], 4);
+            tc::mbar_init(&a2_full[s], 4); tc::mbar_init(&a2_empty[s], 1);
+            tc::mbar_init(&t2_full[s], 1); tc::mbar_init(&t2_empty[s], 4);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+    if (threadIdx.x < 64) { s_b1a[threadIdx.x] = bias1a[threadIdx.x]; s_b1b[threadIdx.x] = bias1b[threadIdx.x]; }
+    // conv1a weights as the B operand of MMA1: row n (output channel), K = 16 (taps 0..8, then zeros)
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int nrow = threadIdx.x - 64;
+        __align__(16) bf16 k[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) k[t] = t < 9 ? w1a[t * 64 + nrow] : __float2bfloat16_rn(0.f);
+        // K slots 9 and 10 multiply a constant 1.0 in the A operand: bias = hi + lo (two bf16 terms,
+        // exact to 2^-17 relative), accumulated in fp32 by the tensor core
+        const float bfull = bias1a[nrow];
+        k[9] = __float2bfloat16_rn(bfull);
+        k[10] = __float2bfloat16_rn(bfull - __bfloat162float(k[9]));
+        uint8_t* row = sW1a + nrow * 128;
+        *reinterpret_cast<uint4*>(row + ((0 ^ (nrow & 7)) << 4)) = *reinterpret_cast<const uint4*>(&k[0]);
+        *reinterpret_cast<uint4*>(row + ((1 ^ (nrow & 7)) << 4)) = *reinterpret_cast<const uint4*>(&k[8]);
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: T1 buffers at 0 and 128 (two 64-col halves each: rows 0-127 / 128-255), T2 at 256 and 320
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(w_full, F1_W1B_BYTES);
+            for (int t = 0; t < 9; ++t) tc::tma_load_3d(sW1b + t * 64 * 128, &tmap_w1b, w_full, 0, 0, t);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: iteration i issues MMA1(i) then MMA2(i-1) =====
+        const uint32_t idesc = tc::make_idesc_bf16(128, 64);
+        bool ok = tc::mbar_wait(w_full, 0, err, 401);
+        const uint64_t dw1a = tc::make_smem_desc_sw128(tc::smem_u32(sW1a), 1024);
+        const uint64_t dw1b = tc::make_smem_desc_sw128(tc::smem_u32(sW1b), 1024);
+        const uint64_t da1_0 = tc::make_smem_desc_sw128(tc::smem_u32(sA1), 1024);
+        const uint64_t da2_0 = tc::make_smem_desc_sw128(tc::smem_u32(sA2), H2_HW * 128);
+        const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        for (int i = 0; ok && i <= my_tiles; ++i) {
+            if (i < my_tiles) {
+                const int b = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                if (!tc::mbar_wait(&a1_full[b], ph, err, 402)) break;
+                if (i >= 2 && !tc::mbar_wait(&t1_empty[b], ph ^ 1, err, 403)) break;
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint64_t da = da1_0 + (uint64_t)((b * F1_A1_BYTES) >> 4);
+                    tc::umma_bf16(tmem_base + (uint32_t)(b * 128), da, dw1a, idesc, 0u);
+                    tc::umma_bf16(tmem_base + (uint32_t)(b * 128 + 64), da + (uint64_t)((128 * 128) >> 4), dw1a, idesc, 0u);
+                    tc::umma_commit(&a1_empty[b]);
+                    tc::umma_commit(&t1_full[b]);
+                }
+                __syncwarp();
+            }
+            if (i >= 1) {
+                const int j = i - 1, b = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                if (!tc::mbar_wait(&a2_full[b], ph, err, 404)) break;
+                if (j >= 2 && !tc::mbar_wait(&t2_empty[b], ph ^ 1, err, 405)) break;
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint64_t da0 = da2_0 + (uint64_t)((b * H2_HALO_STRIDE) >> 4);
+                    const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(b * 64);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
+                            const uint64_t db = dw1b + (uint64_t)((t * 64 * 128 + k * 32) >> 4);
+                            tc::umma_bf16(d_tmem, da, db, idesc, (t | k) ? 1u : 0u);
+                        }
+                    }
+                    tc::umma_commit(&a2_empty[b]);
+                    tc::umma_commit(&t2_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== im2col: halo row r = hy*10 + hx  <->  a1a pixel (y0-1+hy, x0-1+hx); K index = tap =====
+        const int it_ = threadIdx.x - 12 * 32;  // 0..127
+        // rows owned by this thread (tile independent): r0 = it_, r1 = it_ + 128 (< 180 for it_ < 52)
+        const int r0 = it_, r1 = it_ + 128;
+        const int hy0 = r0 / H2_HW, hx0 = r0 - hy0 * H2_HW, hy1 = r1 / H2_HW, hx1 = r1 - hy1 * H2_HW;
+        const bool has1 = r1 < H2_HH * H2_HW;
+        const unsigned short one = 0x3F80;   // bf16 1.0
+        int i = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+            const int b = i & 1;
+            if (i >= 2 && !tc::mbar_wait(&a1_empty[b], ((i >> 1) & 1) ^ 1, err, 406)) break;
+            const int im = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int y0 = (rem / tiles_x) * H2_TH, x0 = (rem % tiles_x) * H2_TW;
+            const uint8_t* ip = img + (size_t)im * h * w;
+            uint8_t* a1 = sA1 + b * F1_A1_BYTES;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (rr == 1 && !has1) break;
+                const int r = rr ? r1 : r0;
+                const int y = y0 - 1 + (rr ? hy1 : hy0), x = x0 - 1 + (rr ? hx1 : hx0);
+                uint32_t kw[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 16 bf16 = K slots 0..15
+                if (y >= 0 && y < h && x >= 0 && x < w) {   // outside the image the whole row stays 0 => conv1a output 0
+                    unsigned short kv[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                        kv[t] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? s_lut[__ldg(&ip[(size_t)yy * w + xx])] : (unsigned short)0;
+                    }
+                    kw[0] = kv[0] | ((uint32_t)kv[1] << 16); kw[1] = kv[2] | ((uint32_t)kv[3] << 16);
+                    kw[2] = kv[4] | ((uint32_t)kv[5] << 16); kw[3] = kv[6] | ((uint32_t)kv[7] << 16);
+                    kw[4] = kv[8] | ((uint32_t)one << 16);   // slot 9 = 1.0 (bias hi)
+                    kw[5] = one;                             // slot 10 = 1.0 (bias lo)
+                }
+                uint8_t* row = a1 + r * 128;
+                *reinterpret_cast<uint4*>(row + ((0 ^ (r & 7)) << 4)) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+                *reinterpret_cast<uint4*>(row + ((1 ^ (r & 7)) << 4)) = make_uint4(kw[4], kw[5], kw[6], kw[7]);
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&a1_full[b]);
+        }
+    } else if (warp >= 8) {
+        // ===== convert: T1 (fp32 conv1a) -> bias, ReLU, bf16 -> conv1b halo tile (128B swizzle) =====
+        const int q = warp & 3;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            if (!tc::mbar_wait(&t1_full[b], ph, err, 407)) break;
+            if (i >= 2 && !tc::mbar_wait(&a2_empty[b], ph ^ 1, err, 408)) break;
+            tc::tc_fence_after();
+            uint8_t* a2 = sA2 + b * H2_HALO_STRIDE;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int r = half * 128 + q * 32 + lane;       // halo row handled by this thread
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 128 + half * 64);
+                uint8_t* row = a2 + r * 128;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(taddr + c0, v);
+                    tc::tmem_ld_wait();
+                    if (r < H2_HH * H2_HW) {   // bias came through the MMA; out-of-image rows are exactly 0
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int chunk = (c0 >> 3) + g;   // 16-byte chunk index 0..7
+                            *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = make_uint4(
+                                tc::pack_bf16x2_relu(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                tc::pack_bf16x2_relu(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                tc::pack_bf16x2_relu(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                tc::pack_bf16x2_relu(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(&t1_empty[b]); tc::mbar_arrive(&a2_full[b]); }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (as conv_tc_halo_kernel, pool fixed on) =====
+        const int q = warp & 3;
+        const int yl = 4 * q + (lane >> 3), xl = lane & 7;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+            const int b = i & 1;
+            const int im = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int y = (rem / tiles_x) * H2_TH + yl, x = (rem % tiles_x) * H2_TW + xl;
+            if (!tc::mbar_wait(&t2_full[b], (i >> 1) & 1, err, 409)) break;
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(b * 64);
+            const bool writer = (y < h) && (x < w) && ((xl | yl) & 1) == 0;
+            const size_t pix = ((size_t)im * (h / 2) + (y >> 1)) * (size_t)(w / 2) + (x >> 1);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(taddr + c0, v);
+                tc::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&s_b1b[c0 + 4 * j4]);
+                    packed[2 * j4] = tc::pack_bf16x2_relu(__uint_as_float(v[4 * j4]) + bb.x, __uint_as_float(v[4 * j4 + 1]) + bb.y);
+                    packed[2 * j4 + 1] = tc::pack_bf16x2_relu(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t u = packed[j];
+                    uint32_t u1 = __shfl_xor_sync(0xffffffffu, u, 1);
+                    __nv_bfloat162 o = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u), *reinterpret_cast<__nv_bfloat162*>(&u1));
+                    u = *reinterpret_cast<uint32_t*>(&o);
+                    uint32_t u8 = __shfl_xor_sync(0xffffffffu, u, 8);
+                    o = __hmax2(o, *reinterpret_cast<__nv_bfloat162*>(&u8));
+                    packed[j] = *reinterpret_cast<uint32_t*>(&o);
+                }
+                if (writer) {
+                    uint4* o = reinterpret_cast<uint4*>(out_bf + pix * 64 + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&t2_empty[b]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out_p1) {
+    if ((h | w) & 1) return GNB_E_INVALID;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNB_CUDA(ctx, cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM));
+        attr_set = true;
+    }
+    const int total = ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n;
+    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+    GNB_KERNEL(ctx, "conv_tc:1a+1b", conv1_fused_kernel<<<grid, F1_THREADS, F1_SMEM, ctx->stream>>>(
+        img, ctx->layers[L1A].w, ctx->layers[L1A].bias, g_wmaps[L1B].w64, ctx->layers[L1B].bias, h, w, n, out_p1, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
 

@@ -125,6 +125,18 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// two fp32 -> packed bf16x2 (lo in bits 0..15), round-to-nearest-even, optional fused ReLU
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
