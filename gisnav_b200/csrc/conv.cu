@@ -291,7 +291,7 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
     cw.n = n; cw.h = h; cw.w = w;
     int rc;
     static const int no_fuse = getenv("GNB_NO_CONV1_FUSION") ? atoi(getenv("GNB_NO_CONV1_FUSION")) : 0;
-    const bool fused1 = ctx->cfg.conv_impl == 0 && !no_fuse;
+    const bool fused1 = ctx->cfg.conv_impl == 0 && !no_fuse && (w % 16) == 0;  // TMA on the u8 image needs a 16-byte row pitch
     if (!fused1 || dense_desc) {
         // standalone conv1a: SIMT path, or the stage hooks that expose the conv1a activation
         dim3 grid(ceil_div(w, C1_TW), ceil_div(h, C1_TH), n);

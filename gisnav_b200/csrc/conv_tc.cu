@@ -382,9 +382,13 @@ static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUten
 #define F1_W1A_BYTES (64 * 128)
 #define F1_W1B_BYTES (9 * 64 * 128)
 #define F1_THREADS 512               // 16 warps: 0 W-loader, 1 MMA, 2 TMEM alloc, 4-7 epilogue, 8-11 convert, 12-15 im2col
-#define F1_SMEM (1024 + F1_W1B_BYTES + F1_W1A_BYTES + 2 * F1_A1_BYTES + 2 * H2_HALO_STRIDE + 512 + 2 * 64 * 4)
+#define F1_PATCH_W 32                 // bytes per patch row (TMA inner box extent must be a multiple of 16 B)
+#define F1_PATCH_H (H2_HH + 2)        // 20 rows: halo of the halo
+#define F1_PATCH_BYTES (F1_PATCH_W * F1_PATCH_H)   // 640
+#define F1_PSTAGES 8
+#define F1_SMEM (1024 + F1_W1B_BYTES + F1_W1A_BYTES + 2 * F1_A1_BYTES + 2 * H2_HALO_STRIDE + 1024 + F1_PSTAGES * F1_PATCH_BYTES)
 
-__global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_t* __restrict__ img, const bf16* __restrict__ w1a,
+__global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_img, const bf16* __restrict__ w1a,
                                                                     const float* __restrict__ bias1a,
                                                                     const __grid_constant__ CUtensorMap tmap_w1b,
                                                                     const float* __restrict__ bias1b, int h, int w, int n_img,
@@ -405,9 +409,12 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
     uint64_t* a2_empty = bars + 11;   // [2] MMA2 done reading A2 (tcgen05.commit)
     uint64_t* t2_full = bars + 13;    // [2] MMA2 -> epilogue     (tcgen05.commit)
     uint64_t* t2_empty = bars + 15;   // [2] epilogue -> MMA2     (4 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-    float* s_b1a = reinterpret_cast<float*>(tmem_slot + 4);
+    uint64_t* p_full = bars + 17;     // [F1_PSTAGES] TMA image patch landed
+    uint64_t* p_empty = bars + 17 + F1_PSTAGES;  // [F1_PSTAGES] im2col done with the patch (4 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17 + 2 * F1_PSTAGES);
+    float* s_b1a = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
     float* s_b1b = s_b1a + 64;
+    uint8_t* sP = reinterpret_cast<uint8_t*>(bars) + 1024;   // [F1_PSTAGES][20 x 32 B] u8 image patches
     __shared__ unsigned short s_lut[256];   // u8 -> bf16(v / 255)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -421,6 +428,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_w1b);
+        tc::tma_prefetch_desc(&tmap_img);
         tc::mbar_init(w_full, 1);
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&a1_full[s], 4); tc::mbar_init(&a1_empty[s], 1);
@@ -428,6 +436,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
             tc::mbar_init(&a2_full[s], 4); tc::mbar_init(&a2_empty[s], 1);
             tc::mbar_init(&t2_full[s], 1); tc::mbar_init(&t2_empty[s], 4);
         }
+        for (int s = 0; s < F1_PSTAGES; ++s) { tc::mbar_init(&p_full[s], 1); tc::mbar_init(&p_empty[s], 4); }
         tc::fence_barrier_init();
     }
     if (warp == 2) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
@@ -458,6 +467,18 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
         if (lane == 0) {
             tc::mbar_arrive_expect_tx(w_full, F1_W1B_BYTES);
             for (int t = 0; t < 9; ++t) tc::tma_load_3d(sW1b + t * 64 * 128, &tmap_w1b, w_full, 0, 0, t);
+            // u8 image patches (20 rows x 32 px, origin (y0-2, x0-2); OOB zero fill = image zero padding)
+            int i = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+                const int s = i % F1_PSTAGES;
+                if (i >= F1_PSTAGES && !tc::mbar_wait(&p_empty[s], ((i / F1_PSTAGES) & 1) ^ 1, err, 410)) break;
+                const int im = tile / tiles_per_img, rem = tile % tiles_per_img;
+                const int y0 = (rem / tiles_x) * H2_TH, x0 = (rem % tiles_x) * H2_TW;
+                tc::mbar_arrive_expect_tx(&p_full[s], F1_PATCH_BYTES);
+                // the image is viewed as uint32 words; the box starts on a 16-byte boundary at or left of x0-2
+                const int sx = ((x0 - 2 + 16) & ~15) - 16;
+                tc::tma_load_3d(sP + s * F1_PATCH_BYTES, &tmap_img, &p_full[s], sx >> 2, y0 - 2, im);
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: iteration i issues MMA1(i) then MMA2(i-1) =====
@@ -518,25 +539,24 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
         const unsigned short one = 0x3F80;   // bf16 1.0
         int i = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
-            const int b = i & 1;
+            const int b = i & 1, ps = i % F1_PSTAGES;
             if (i >= 2 && !tc::mbar_wait(&a1_empty[b], ((i >> 1) & 1) ^ 1, err, 406)) break;
-            const int im = tile / tiles_per_img, rem = tile % tiles_per_img;
+            if (!tc::mbar_wait(&p_full[ps], (i / F1_PSTAGES) & 1, err, 411)) break;
+            const int rem = tile % tiles_per_img;
             const int y0 = (rem / tiles_x) * H2_TH, x0 = (rem % tiles_x) * H2_TW;
-            const uint8_t* ip = img + (size_t)im * h * w;
+            const uint8_t* patch = sP + ps * F1_PATCH_BYTES + ((x0 - 2) - (((x0 - 2 + 16) & ~15) - 16));  // column of x0-2 in the box
             uint8_t* a1 = sA1 + b * F1_A1_BYTES;
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 if (rr == 1 && !has1) break;
                 const int r = rr ? r1 : r0;
-                const int y = y0 - 1 + (rr ? hy1 : hy0), x = x0 - 1 + (rr ? hx1 : hx0);
+                const int hy = rr ? hy1 : hy0, hx = rr ? hx1 : hx0;
+                const int y = y0 - 1 + hy, x = x0 - 1 + hx;
                 uint32_t kw[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 16 bf16 = K slots 0..15
                 if (y >= 0 && y < h && x >= 0 && x < w) {   // outside the image the whole row stays 0 => conv1a output 0
                     unsigned short kv[9];
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-                        kv[t] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? s_lut[__ldg(&ip[(size_t)yy * w + xx])] : (unsigned short)0;
-                    }
+                    for (int t = 0; t < 9; ++t) kv[t] = s_lut[patch[(hy + t / 3) * F1_PATCH_W + hx + t % 3]];
                     kw[0] = kv[0] | ((uint32_t)kv[1] << 16); kw[1] = kv[2] | ((uint32_t)kv[3] << 16);
                     kw[2] = kv[4] | ((uint32_t)kv[5] << 16); kw[3] = kv[6] | ((uint32_t)kv[7] << 16);
                     kw[4] = kv[8] | ((uint32_t)one << 16);   // slot 9 = 1.0 (bias hi)
@@ -548,7 +568,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
             }
             tc::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&a1_full[b]);
+            if (lane == 0) { tc::mbar_arrive(&a1_full[b]); tc::mbar_arrive(&p_empty[ps]); }
         }
     } else if (warp >= 8) {
         // ===== convert: T1 (fp32 conv1a) -> bias, ReLU, bf16 -> conv1b halo tile (128B swizzle) =====
@@ -563,6 +583,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
             uint8_t* a2 = sA2 + b * H2_HALO_STRIDE;
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
+                if (half * 128 + q * 32 >= H2_HH * H2_HW) continue;  // rows 192..255 hold no halo pixel (warp-uniform)
                 const int r = half * 128 + q * 32 + lane;       // halo row handled by this thread
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 128 + half * 64);
                 uint8_t* row = a2 + r * 128;
@@ -642,16 +663,26 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const uint8_
 }
 
 int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out_p1) {
-    if ((h | w) & 1) return GNB_E_INVALID;
+    if (((h | w) & 1) || (w % 16)) return GNB_E_INVALID;   // TMA: row pitch must be a multiple of 16 bytes
     static bool attr_set = false;
     if (!attr_set) {
         GNB_CUDA(ctx, cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM));
         attr_set = true;
     }
+    gnb_encode_tiled_fn fn = gnb_get_encode_tiled(ctx);
+    if (!fn) return GNB_E_CUDA;
+    CUtensorMap timg;
+    const cuuint64_t gdim[3] = {(cuuint64_t)w / 4, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t gstr[2] = {(cuuint64_t)w, (cuuint64_t)w * h};
+    const cuuint32_t box[3] = {F1_PATCH_W / 4, F1_PATCH_H, 1}, es[3] = {1, 1, 1};
+    CUresult r = fn(&timg, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(img), gdim, gstr, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { GNB_SET_ERR(ctx, "cuTensorMapEncodeTiled(u8 image) failed: %d", (int)r); return GNB_E_CUDA; }
     const int total = ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n;
     const int grid = total < ctx->sm_count ? total : ctx->sm_count;
     GNB_KERNEL(ctx, "conv_tc:1a+1b", conv1_fused_kernel<<<grid, F1_THREADS, F1_SMEM, ctx->stream>>>(
-        img, ctx->layers[L1A].w, ctx->layers[L1A].bias, g_wmaps[L1B].w64, ctx->layers[L1B].bias, h, w, n, out_p1, gnb_tc_err_dev(ctx)));
+        timg, ctx->layers[L1A].w, ctx->layers[L1A].bias, g_wmaps[L1B].w64, ctx->layers[L1B].bias, h, w, n, out_p1, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
 

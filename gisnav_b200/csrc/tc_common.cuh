@@ -25,25 +25,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware (up to ~hint ns) instead of spinning
+// through the issue slots that the working warps of the same SM sub-partition need.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x4000u)
         : "memory");
     return ok;
 }
 // Bounded wait: a protocol bug must not hang the GPU.  On timeout the error word (host-mapped) is
-// set and false is returned; callers fall through to their teardown.
+// set and false is returned; callers fall through to their teardown.  The clock is read only every
+// 32 failed probes to keep the wait loop light.
 #define TC_WAIT_TIMEOUT_CYCLES 600000000LL
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err, int code) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > TC_WAIT_TIMEOUT_CYCLES) {
+        if (((++spins) & 31u) == 0 && clock64() - t0 > TC_WAIT_TIMEOUT_CYCLES) {
             if (err) *err = code;
             return false;
         }
