@@ -120,7 +120,9 @@ static int alloc_workspace(gnb_ctx* ctx) {
     cw.cap_images = c.max_batch;
     cw.cap_pixels = px;
     int rc = 0;
-    rc |= dalloc(ctx, &cw.img, n * px);
+    rc |= dalloc(ctx, &cw.img_a, n * px);
+    rc |= dalloc(ctx, &cw.img_b, n * px);
+    cw.img = cw.img_a;
     rc |= dalloc(ctx, &cw.a1a, n * px * 64);
     rc |= dalloc(ctx, &cw.p1, n * px / 4 * 64);
     rc |= dalloc(ctx, &cw.a2a, n * px / 4 * 64);
@@ -177,7 +179,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
     gnb_conv_free(ctx);
     gnb_match_free(ctx);
     ConvWorkspace& cw = ctx->cw;
-    void* ptrs[] = {cw.img, cw.a1a, cw.p1, cw.a2a, cw.p2, cw.a3a, cw.p3, cw.a4a, cw.a4b, cw.apa, cw.ada, cw.semi,
+    void* ptrs[] = {cw.img_a, cw.img_b, cw.a1a, cw.p1, cw.a2a, cw.p2, cw.a3a, cw.p3, cw.a4a, cw.a4b, cw.apa, cw.ada, cw.semi,
                     cw.score, cw.dense, ctx->cand_keys, ctx->cand_count, ctx->kp_xy, ctx->kp_score, ctx->kp_count,
                     ctx->desc_f32, ctx->mproj, ctx->mlogit, ctx->row_lse, ctx->best_val, ctx->best_idx, ctx->match_idx,
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
@@ -192,6 +194,10 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
         for (auto& p : ps->pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
         delete ps;
     }
+    if (ctx->ev_frames) cudaEventDestroy(ctx->ev_frames);
+    if (ctx->ev_tiles) cudaEventDestroy(ctx->ev_tiles);
+    if (ctx->ev_params) cudaEventDestroy(ctx->ev_params);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -231,8 +237,12 @@ extern "C" int gnb_create(const gnb_config* cfg, const void* weights, size_t nby
         return code;
     };
     if (cudaSetDevice(device) != cudaSuccess) { GNB_SET_ERR(ctx, "cudaSetDevice failed"); return fail(GNB_E_CUDA); }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        GNB_SET_ERR(ctx, "stream create failed");
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_frames, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_tiles, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_params, cudaEventDisableTiming) != cudaSuccess) {
+        GNB_SET_ERR(ctx, "stream create failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(GNB_E_CUDA);
     }
     // weight blob: 16-byte header + floats (gisnav_b200/weights.py)
@@ -420,20 +430,33 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
     if ((rc = check_image(ctx, hq, wq)) || (rc = check_image(ctx, ht, wt))) return rc;
     const int sb = ctx->cfg.max_batch;
     const cudaMemcpyKind kin = kind_in(on_device);
-    // small per-pair parameters first so they overlap with the first conv pass
-    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kmat, k9, sizeof(double) * 9 * batch, kin, ctx->stream));
-    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->affine, affine12, sizeof(double) * 12 * batch, kin, ctx->stream));
-    if (dems) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dems, (size_t)batch * ht * wt, kin, ctx->stream));
+    // staging: all copies go to the copy stream; the compute stream waits on events, so the raster /
+    // DEM / parameter copies overlap with the conv pass over the query frames
+    cudaStream_t cs = ctx->copy_stream;
+    ConvWorkspace& cw = ctx->cw;
+    GNB_CUDA(ctx, cudaMemcpyAsync(cw.img_a, frames, (size_t)batch * hq * wq, kin, cs));
+    GNB_CUDA(ctx, cudaEventRecord(ctx->ev_frames, cs));
+    GNB_CUDA(ctx, cudaMemcpyAsync(cw.img_b, tiles, (size_t)batch * ht * wt, kin, cs));
+    GNB_CUDA(ctx, cudaEventRecord(ctx->ev_tiles, cs));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kmat, k9, sizeof(double) * 9 * batch, kin, cs));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->affine, affine12, sizeof(double) * 12 * batch, kin, cs));
+    if (dems) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dems, (size_t)batch * ht * wt, kin, cs));
+    GNB_CUDA(ctx, cudaEventRecord(ctx->ev_params, cs));
     // query frames -> slots [0, batch)
-    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.img, frames, (size_t)batch * hq * wq, kin, ctx->stream));
+    GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_frames, 0));
+    cw.img = cw.img_a;
     if ((rc = gnb_conv_forward(ctx, batch, hq, wq, 0))) return rc;
     if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, hq, wq, 0))) return rc;
     if ((rc = gnb_describe(ctx, batch, hq, wq, 0))) return rc;
     // reference rasters -> slots [max_batch, max_batch + batch)
-    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.img, tiles, (size_t)batch * ht * wt, kin, ctx->stream));
-    if ((rc = gnb_conv_forward(ctx, batch, ht, wt, 0))) return rc;
+    GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tiles, 0));
+    cw.img = cw.img_b;
+    rc = gnb_conv_forward(ctx, batch, ht, wt, 0);
+    cw.img = cw.img_a;
+    if (rc) return rc;
     if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, ht, wt, sb))) return rc;
     if ((rc = gnb_describe(ctx, batch, ht, wt, sb))) return rc;
+    GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_params, 0));
     if ((rc = gnb_match_project(ctx, 0, batch))) return rc;
     if ((rc = gnb_match_project(ctx, sb, batch))) return rc;
     if ((rc = gnb_match_pairs(ctx, batch, 0, sb))) return rc;

@@ -26,7 +26,8 @@ struct ConvLayer {
 struct ConvWorkspace {
     int cap_images;       // images per pass
     size_t cap_pixels;    // max h*w per image
-    uint8_t* img;         // [n][h][w]
+    uint8_t* img;         // [n][h][w]  input of the current pass (points at img_a or img_b)
+    uint8_t *img_a, *img_b; // two staging buffers so the second H2D copy overlaps the first pass
     bf16 *a1a, *p1, *a2a, *p2, *a3a, *p3, *a4a, *a4b, *apa, *ada;
     float* semi;          // [n][hc][wc][65]
     float* score;         // [n][h][w]
@@ -48,6 +49,8 @@ struct gnb_ctx {
     int device;
     int sm_count;
     cudaStream_t stream;
+    cudaStream_t copy_stream;           // H2D staging of the batch path, overlapped with compute
+    cudaEvent_t ev_frames, ev_tiles, ev_params;
     char err[512];
     int64_t launches;
     ConvLayer layers[GNB_NUM_LAYERS];
