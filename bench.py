@@ -373,10 +373,10 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="pairs per step per GPU")
     ap.add_argument("--keypoints", type=int, default=1024)
     ap.add_argument("--ransac-iters", type=int, default=2048)
     ap.add_argument("--cpu-pairs", type=int, default=4, help="pairs timed on the host cores for cpu_baseline (N=1 only)")

@@ -40,6 +40,7 @@ class GnbConfig(C.Structure):
         ("max_image_w", C.c_int32),
         ("conv_impl", C.c_int32),
         ("match_impl", C.c_int32),
+        ("tile_cache", C.c_int32),
     ]
 
 
@@ -78,6 +79,8 @@ SIGNATURES = {
     "gnb_solve_pnp": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, C.POINTER(_I)]),
     "gnb_geodetic_tail": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),
     "gnb_pose_batch": (_I, [_VP, _I, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, C.POINTER(GnbPoseResult)]),
+    "gnb_pose_candidates": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, C.POINTER(GnbPoseResult), C.POINTER(_I)]),
+    "gnb_cache_clear": (_I, [_VP]),
     "gnb_dense": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "gnb_layer_activation": (_I, [_VP, C.c_char_p, _VP, C.c_size_t]),
     "gnb_select_keypoints": (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, C.POINTER(_I)]),

@@ -30,6 +30,7 @@ class Config:
     max_image_w: int = 1280
     conv_impl: Optional[int] = None  # 0 tcgen05 (product), 1 SIMT validation kernel; None = library default
     match_impl: Optional[int] = None
+    tile_cache: int = 32  # reference-raster feature cache entries
 
     def __post_init__(self):
         if self.conv_impl is None or self.match_impl is None:

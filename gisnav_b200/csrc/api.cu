@@ -79,6 +79,7 @@ extern "C" int gnb_default_config(gnb_config* cfg) {
     cfg->max_image_w = 1280;
     cfg->conv_impl = 0;   // tcgen05 implicit GEMM
     cfg->match_impl = 0;  // tcgen05 descriptor GEMM
+    cfg->tile_cache = 32;
     return GNB_OK;
 }
 
@@ -164,7 +165,17 @@ static int alloc_workspace(gnb_ctx* ctx) {
     rc |= dalloc(ctx, &ctx->affine, n * 12);
     rc |= dalloc(ctx, &ctx->dem, n * px);
     rc |= dalloc(ctx, &ctx->out_dev, n);
+    ctx->cache_cap = c.tile_cache > (int)n ? c.tile_cache : (int)n;
+    const size_t cc = ctx->cache_cap;
+    rc |= dalloc(ctx, &ctx->c_kp_xy, cc * k * 2);
+    rc |= dalloc(ctx, &ctx->c_kp_count, cc);
+    rc |= dalloc(ctx, &ctx->c_mproj, cc * k * 256);
+    rc |= dalloc(ctx, &ctx->c_mlogit, cc * k);
     if (rc) return GNB_E_CUDA;
+    ctx->cache_ids = new long long[cc];
+    ctx->cache_lru = new unsigned long long[cc];
+    for (size_t i = 0; i < cc; ++i) { ctx->cache_ids[i] = -1; ctx->cache_lru[i] = 0; }
+    ctx->cache_clock = 0;
     GNB_CUDA(ctx, cudaMemset(ctx->kp_count, 0, slots * sizeof(int)));
     GNB_CUDA(ctx, cudaMemset(ctx->mproj, 0, slots * k * 256 * sizeof(bf16)));
     GNB_CUDA(ctx, cudaMemset(ctx->kp_xy, 0, slots * k * 2 * sizeof(float)));
@@ -184,10 +195,12 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->desc_f32, ctx->mproj, ctx->mlogit, ctx->row_lse, ctx->best_val, ctx->best_idx, ctx->match_idx,
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
-                    ctx->stage_b};
+                    ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
+    delete[] ctx->cache_ids;
+    delete[] ctx->cache_lru;
     if (ctx->prof) {
         ProfState* ps = static_cast<ProfState*>(ctx->prof);
         for (auto& r : ps->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -470,6 +483,99 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
             return GNB_E_CAPACITY;
         }
         if (results[b].status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM in pair %d", b); return GNB_E_RANGE; }
+    }
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// candidate search with a reference-raster feature cache
+extern "C" int gnb_cache_clear(gnb_ctx* ctx) {
+    if (!ctx) return GNB_E_INVALID;
+    for (int i = 0; i < ctx->cache_cap; ++i) { ctx->cache_ids[i] = -1; ctx->cache_lru[i] = 0; }
+    return GNB_OK;
+}
+
+static void cache_copy(gnb_ctx* ctx, int entry, int slot, bool to_cache) {
+    const size_t k = ctx->cfg.max_keypoints;
+    auto cp = [&](void* cache_p, void* slot_p, size_t bytes) {
+        cudaMemcpyAsync(to_cache ? cache_p : slot_p, to_cache ? slot_p : cache_p, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    };
+    cp(ctx->c_kp_xy + (size_t)entry * k * 2, ctx->kp_xy + (size_t)slot * k * 2, k * 2 * sizeof(float));
+    cp(ctx->c_kp_count + entry, ctx->kp_count + slot, sizeof(int));
+    cp(ctx->c_mproj + (size_t)entry * k * 256, ctx->mproj + (size_t)slot * k * 256, k * 256 * sizeof(bf16));
+    cp(ctx->c_mlogit + (size_t)entry * k, ctx->mlogit + (size_t)slot * k, k * sizeof(float));
+}
+
+extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* tiles, int ht,
+                                   int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9, const double* affine12,
+                                   gnb_pose_result* results, int* n_cache_hits) {
+    if (!ctx || !frame || !tiles || !k9 || !affine12 || !results || n_tiles < 1) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_tiles > ctx->cfg.max_batch) { GNB_SET_ERR(ctx, "n_tiles %d exceeds max_batch %d", n_tiles, ctx->cfg.max_batch); return GNB_E_CAPACITY; }
+    int rc;
+    if ((rc = check_image(ctx, hq, wq)) || (rc = check_image(ctx, ht, wt))) return rc;
+    const int sb = ctx->cfg.max_batch;
+    ConvWorkspace& cw = ctx->cw;
+    // cache lookup: entry[i] = cache entry that will hold raster i's features; hit[i] = already there
+    std::vector<int> entry(n_tiles), hit(n_tiles, 0);
+    std::vector<char> used(ctx->cache_cap, 0);
+    int hits = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        entry[i] = -1;
+        if (tile_ids && tile_ids[i] >= 0)
+            for (int e = 0; e < ctx->cache_cap; ++e)
+                if (ctx->cache_ids[e] == tile_ids[i] && !used[e]) { entry[i] = e; hit[i] = 1; used[e] = 1; ++hits; break; }
+    }
+    for (int i = 0; i < n_tiles; ++i) {
+        if (entry[i] >= 0) continue;
+        int best = -1;
+        for (int e = 0; e < ctx->cache_cap; ++e)   // least recently used entry not claimed by this call
+            if (!used[e] && (best < 0 || ctx->cache_lru[e] < ctx->cache_lru[best])) best = e;
+        entry[i] = best; used[best] = 1;
+        ctx->cache_ids[best] = (tile_ids && tile_ids[i] >= 0) ? tile_ids[i] : -1;
+    }
+    for (int i = 0; i < n_tiles; ++i) ctx->cache_lru[entry[i]] = ++ctx->cache_clock;
+    if (n_cache_hits) *n_cache_hits = hits;
+    // parameters: one K for all pairs
+    std::vector<double> kk((size_t)n_tiles * 9);
+    for (int i = 0; i < n_tiles; ++i) memcpy(&kk[(size_t)i * 9], k9, 9 * sizeof(double));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kmat, kk.data(), kk.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->affine, affine12, sizeof(double) * 12 * n_tiles, cudaMemcpyHostToDevice, ctx->stream));
+    if (dems) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dems, (size_t)n_tiles * ht * wt, cudaMemcpyHostToDevice, ctx->stream));
+    // query frame -> slot 0
+    GNB_CUDA(ctx, cudaMemcpyAsync(cw.img_a, frame, (size_t)hq * wq, cudaMemcpyHostToDevice, ctx->stream));
+    cw.img = cw.img_a;
+    if ((rc = gnb_conv_forward(ctx, 1, hq, wq, 0))) return rc;
+    if ((rc = gnb_kp_select(ctx, cw.score, 1, hq, wq, 0))) return rc;
+    if ((rc = gnb_describe(ctx, 1, hq, wq, 0))) return rc;
+    if ((rc = gnb_match_project(ctx, 0, 1))) return rc;
+    // rasters that missed the cache: one compact batch -> slots [sb, sb + m)
+    std::vector<int> miss;
+    for (int i = 0; i < n_tiles; ++i) if (!hit[i]) miss.push_back(i);
+    const int m = (int)miss.size();
+    if (m > 0) {
+        for (int j = 0; j < m; ++j)
+            GNB_CUDA(ctx, cudaMemcpyAsync(cw.img_b + (size_t)j * ht * wt, tiles + (size_t)miss[j] * ht * wt, (size_t)ht * wt,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        cw.img = cw.img_b;
+        rc = gnb_conv_forward(ctx, m, ht, wt, 0);
+        cw.img = cw.img_a;
+        if (rc) return rc;
+        if ((rc = gnb_kp_select(ctx, cw.score, m, ht, wt, sb))) return rc;
+        if ((rc = gnb_describe(ctx, m, ht, wt, sb))) return rc;
+        if ((rc = gnb_match_project(ctx, sb, m))) return rc;
+        for (int j = 0; j < m; ++j) cache_copy(ctx, entry[miss[j]], sb + j, true);
+    }
+    for (int i = 0; i < n_tiles; ++i) cache_copy(ctx, entry[i], sb + i, false);
+    GNB_CUDA(ctx, cudaGetLastError());
+    if ((rc = gnb_match_pairs(ctx, n_tiles, 0, sb, 0))) return rc;
+    if ((rc = gnb_pnp_pairs(ctx, n_tiles, ht, wt, dems ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1, 0))) return rc;
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut) * n_tiles, cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_SYNC(ctx);
+    for (int b = 0; b < n_tiles; ++b) {
+        pairout_to_result(ctx->out_host[b], &results[b]);
+        if (results[b].n_kp_qry < 0 || results[b].n_kp_ref < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); return GNB_E_CAPACITY; }
+        if (results[b].status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM in candidate %d", b); return GNB_E_RANGE; }
     }
     return GNB_OK;
 }

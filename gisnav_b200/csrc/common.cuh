@@ -95,6 +95,15 @@ struct gnb_ctx {
     size_t stage_a_floats;
     float* stage_b;
     size_t stage_b_floats;
+    // reference-raster feature cache (pose_node.py:226-241 caches the raster's features per stamp)
+    int cache_cap;
+    long long* cache_ids;           // host [cache_cap], -1 = free
+    unsigned long long* cache_lru;  // host [cache_cap]
+    unsigned long long cache_clock;
+    float* c_kp_xy;                 // [cache_cap][K][2]
+    int* c_kp_count;                // [cache_cap]
+    bf16* c_mproj;                  // [cache_cap][K][256]
+    float* c_mlogit;                // [cache_cap][K]
     // profiling
     int prof_on;
     void* prof;  // ProfState*
@@ -164,13 +173,13 @@ void gnb_match_free(gnb_ctx* ctx);
 // project descriptors of `n_slots` consecutive slots
 int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots);
 // match slot_a[p] against slot_b[p] for p in [0, pairs): fills match_idx/score/count + mkp_*
-int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0);
+int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a = 1);
 int gnb_match_tc_init(gnb_ctx* ctx);
-int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int pass);
+int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass);
 
 // pnp.cu
 int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, int ref_h, int ref_w, int do_tail,
-                  int min_matches, int use_kp_counts);
+                  int min_matches, int use_kp_counts, int stride_a = 1);
 int gnb_tail_device(gnb_ctx* ctx, const double* r9, const double* t3, const double* affine12, int ref_h, int ref_w,
                     double* ecef3, double* quat4, double* lla3);
 int gnb_ensure_stage(gnb_ctx* ctx, size_t floats_a, size_t floats_b);

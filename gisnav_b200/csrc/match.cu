@@ -111,14 +111,16 @@ int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots) {
 template <int PASS>
 __global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ mproj, const float* __restrict__ mlogit,
                                                        const int* __restrict__ kp_count, int k_cap, int slot_a0,
-                                                       int slot_b0, float* __restrict__ row_lse,
+                                                       int stride_a, int slot_b0, int max_pairs, float* __restrict__ row_lse,
                                                        float* __restrict__ best_val, int* __restrict__ best_idx) {
     extern __shared__ float smf[];
     float* As = smf;              // [256][64]  (k-major, transposed)
     float* Bs = smf + 256 * 64;   // [256][64]
     const int pair = blockIdx.y, side = blockIdx.z;
-    const int slot_r = side == 0 ? slot_a0 + pair : slot_b0 + pair;
-    const int slot_c = side == 0 ? slot_b0 + pair : slot_a0 + pair;
+    // data slots (a side may be shared by all pairs: stride_a = 0) and per-(pair, side) result rows
+    const int slot_a = slot_a0 + pair * stride_a, slot_b = slot_b0 + pair;
+    const int slot_r = side == 0 ? slot_a : slot_b, slot_c = side == 0 ? slot_b : slot_a;
+    const int rs_r = side == 0 ? pair : max_pairs + pair, rs_c = side == 0 ? max_pairs + pair : pair;
     const int nr = max(kp_count[slot_r], 0), nc = max(kp_count[slot_c], 0);
     const int r0 = blockIdx.x * 64;
     if (r0 >= nr) return;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ 
     for (int r = 0; r < 4; ++r) {
         run_max[r] = -INFINITY; run_sum[r] = 0.f; bv[r] = -INFINITY; bi[r] = -1;
         const int row = r0 + ty * 4 + r;
-        rl[r] = (PASS == 1 && row < nr) ? row_lse[(size_t)slot_r * k_cap + row] : 0.f;
+        rl[r] = (PASS == 1 && row < nr) ? row_lse[(size_t)rs_r * k_cap + row] : 0.f;
         la[r] = (PASS == 1 && row < nr) ? mlogit[(size_t)slot_r * k_cap + row] : 0.f;
     }
     for (int c0 = 0; c0 < nc; c0 += 64) {
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ 
                     const int col = c0 + tx * 4 + c;
                     if (col < nc) {
                         const float s = acc[r][c];
-                        const float cl = row_lse[(size_t)slot_c * k_cap + col];
+                        const float cl = row_lse[(size_t)rs_c * k_cap + col];
                         const float lb = mlogit[(size_t)slot_c * k_cap + col];
                         // side 0: rows are a (softmax over dim 1 uses rl), side 1: rows are b
                         const float t_row = __fsub_rn(s, rl[r]), t_col = __fsub_rn(s, cl);
@@ -214,8 +216,8 @@ __global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ 
         for (int r = 0; r < 4; ++r) {
             const int row = r0 + ty * 4 + r;
             if (row < nr) {
-                if (PASS == 0) row_lse[(size_t)slot_r * k_cap + row] = run_max[r] + logf(run_sum[r]);
-                else { best_val[(size_t)slot_r * k_cap + row] = bv[r]; best_idx[(size_t)slot_r * k_cap + row] = bi[r]; }
+                if (PASS == 0) row_lse[(size_t)rs_r * k_cap + row] = run_max[r] + logf(run_sum[r]);
+                else { best_val[(size_t)rs_r * k_cap + row] = bv[r]; best_idx[(size_t)rs_r * k_cap + row] = bi[r]; }
             }
         }
     }
@@ -224,13 +226,14 @@ __global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ 
 // mutual check + threshold + ordered compaction; one CTA per pair.
 __global__ void __launch_bounds__(1024) mutual_kernel(const float* __restrict__ best_val, const int* __restrict__ best_idx,
                                                       const int* __restrict__ kp_count, const float* __restrict__ kp_xy,
-                                                      int k_cap, int slot_a0, int slot_b0, float thr,
+                                                      int k_cap, int slot_a0, int stride_a, int slot_b0, int max_pairs, float thr,
                                                       int* __restrict__ match_idx, float* __restrict__ match_score,
                                                       int* __restrict__ match_count, float* __restrict__ mkp_qry,
                                                       float* __restrict__ mkp_ref) {
     __shared__ int warp_sums[32];
     __shared__ int s_base;
-    const int pair = blockIdx.x, sa = slot_a0 + pair, sb = slot_b0 + pair;
+    const int pair = blockIdx.x, sa = slot_a0 + pair * stride_a, sb = slot_b0 + pair;
+    const int ra = pair, rb = max_pairs + pair;  // result rows of the two sides
     const int na = max(kp_count[sa], 0), nb = max(kp_count[sb], 0);
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
@@ -240,9 +243,9 @@ __global__ void __launch_bounds__(1024) mutual_kernel(const float* __restrict__ 
         int j = -1;
         float ms = 0.f;
         if (i < na && nb > 0) {
-            j = best_idx[(size_t)sa * k_cap + i];
-            if (j >= 0 && best_idx[(size_t)sb * k_cap + j] == i) {
-                ms = expf(best_val[(size_t)sa * k_cap + i]);
+            j = best_idx[(size_t)ra * k_cap + i];
+            if (j >= 0 && best_idx[(size_t)rb * k_cap + j] == i) {
+                ms = expf(best_val[(size_t)ra * k_cap + i]);
                 ok = ms > thr;
             }
         }
@@ -273,12 +276,13 @@ __global__ void __launch_bounds__(1024) mutual_kernel(const float* __restrict__ 
     if (threadIdx.x == 0) match_count[pair] = s_base;
 }
 
-int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0) {
+int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a) {
+    const int mp = ctx->cfg.max_batch;
     const int k = ctx->cfg.max_keypoints;
     if (ctx->cfg.match_impl == 0) {
         int rc;
-        if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, 0))) return rc;
-        if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, 1))) return rc;
+        if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, stride_a, 0))) return rc;
+        if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, stride_a, 1))) return rc;
     } else {
         const size_t smem = 2 * 256 * 64 * sizeof(float);
         static bool attr_set = false;
@@ -288,13 +292,13 @@ int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0) {
             attr_set = true;
         }
         dim3 grid(ceil_div(k, 64), pairs, 2);
-        GNB_KERNEL(ctx, "match_rows_simt<0>", match_rows_simt<0><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0,
+        GNB_KERNEL(ctx, "match_rows_simt<0>", match_rows_simt<0><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
                                                              ctx->row_lse, ctx->best_val, ctx->best_idx));
-        GNB_KERNEL(ctx, "match_rows_simt<1>", match_rows_simt<1><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0,
+        GNB_KERNEL(ctx, "match_rows_simt<1>", match_rows_simt<1><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
                                                              ctx->row_lse, ctx->best_val, ctx->best_idx));
     }
     GNB_KERNEL(ctx, "mutual_kernel", mutual_kernel<<<pairs, 1024, 0, ctx->stream>>>(ctx->best_val, ctx->best_idx, ctx->kp_count, ctx->kp_xy, k, slot_a0,
-                                                   slot_b0, ctx->cfg.match_threshold, ctx->match_idx, ctx->match_score,
+                                                   stride_a, slot_b0, mp, ctx->cfg.match_threshold, ctx->match_idx, ctx->match_score,
                                                    ctx->match_count, ctx->mkp_qry, ctx->mkp_ref));
     return GNB_OK;
 }

@@ -78,12 +78,13 @@ int gnb_tc_err_check(gnb_ctx* ctx) {
 
 template <int PASS>
 __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mlogit,
-                                                        const int* __restrict__ kp_count, int k_cap, int slot_a0, int slot_b0,
+                                                        const int* __restrict__ kp_count, int k_cap, int slot_a0, int stride_a, int slot_b0, int max_pairs,
                                                         float* __restrict__ row_lse, float* __restrict__ best_val,
                                                         int* __restrict__ best_idx, int* err) {
     const int pair = blockIdx.y, side = blockIdx.z;
-    const int slot_r = side == 0 ? slot_a0 + pair : slot_b0 + pair;
-    const int slot_c = side == 0 ? slot_b0 + pair : slot_a0 + pair;
+    const int slot_a = slot_a0 + pair * stride_a, slot_b = slot_b0 + pair;
+    const int slot_r = side == 0 ? slot_a : slot_b, slot_c = side == 0 ? slot_b : slot_a;
+    const int rs_r = side == 0 ? pair : max_pairs + pair, rs_c = side == 0 ? max_pairs + pair : pair;
     const int nr = max(kp_count[slot_r], 0), nc = max(kp_count[slot_c], 0);
     const int r0 = blockIdx.x * MT_BM;
     if (r0 >= nr || nc == 0) return;  // uniform exit before any barrier / TMEM allocation
@@ -175,14 +176,14 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
         float run_max = -INFINITY, run_sum = 0.f, bv = -INFINITY;
         int bi = -1;
         float rl = 0.f, la = 0.f;
-        if (PASS == 1 && row < nr) { rl = row_lse[(size_t)slot_r * k_cap + row]; la = mlogit[(size_t)slot_r * k_cap + row]; }
+        if (PASS == 1 && row < nr) { rl = row_lse[(size_t)rs_r * k_cap + row]; la = mlogit[(size_t)slot_r * k_cap + row]; }
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j % MT_STAGES;
             const uint32_t ph = (j / MT_STAGES) & 1;
             const int c0 = j * MT_BN;
             if (PASS == 1) {
                 const int col = c0 + et;
-                s_cl[s * MT_BN + et] = col < nc ? row_lse[(size_t)slot_c * k_cap + col] : 0.f;
+                s_cl[s * MT_BN + et] = col < nc ? row_lse[(size_t)rs_c * k_cap + col] : 0.f;
                 s_lb[s * MT_BN + et] = col < nc ? mlogit[(size_t)slot_c * k_cap + col] : 0.f;
                 tc::named_bar_sync(1, 128);
             }
@@ -227,8 +228,8 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
             if (lane == 0) tc::mbar_arrive(&t_empty[s]);
         }
         if (row < nr) {
-            if (PASS == 0) row_lse[(size_t)slot_r * k_cap + row] = run_max + logf(run_sum);
-            else { best_val[(size_t)slot_r * k_cap + row] = bv; best_idx[(size_t)slot_r * k_cap + row] = bi; }
+            if (PASS == 0) row_lse[(size_t)rs_r * k_cap + row] = run_max + logf(run_sum);
+            else { best_val[(size_t)rs_r * k_cap + row] = bv; best_idx[(size_t)rs_r * k_cap + row] = bi; }
         }
     }
     tc::tc_fence_before();
@@ -253,14 +254,14 @@ int gnb_match_tc_init(gnb_ctx* ctx) {
     return GNB_OK;
 }
 
-int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int pass) {
+int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass) {
     const int k = ctx->cfg.max_keypoints;
     dim3 grid(ceil_div(k, MT_BM), pairs, 2);
     if (pass == 0)
         GNB_KERNEL(ctx, "match_rows_tc<0>", match_rows_tc<0><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
     else
         GNB_KERNEL(ctx, "match_rows_tc<1>", match_rows_tc<1><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, slot_b0, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
     return GNB_OK;
 }

@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(
     const float* __restrict__ obj, const float* __restrict__ img, const int* __restrict__ match_count, int k_cap,
     const double* __restrict__ kmat, const double* __restrict__ affine, int iters, float thr_px, int min_matches,
     int refine, const float* __restrict__ hyp, const int* __restrict__ hyp_count, const int* __restrict__ range_flag,
-    const int* __restrict__ kp_count, int slot_a0, int slot_b0, int ref_h, int ref_w, int do_tail,
+    const int* __restrict__ kp_count, int slot_a0, int stride_a, int slot_b0, int ref_h, int ref_w, int do_tail,
     uint8_t* __restrict__ inlier_mask, PairOut* __restrict__ out) {
     __shared__ int s_best_c[FIN_THREADS / 32], s_best_h[FIN_THREADS / 32];
     __shared__ int s_winner_h, s_winner_c, s_ninl;
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(
     const int n = match_count[pair];
     PairOut* po = out + pair;
     if (tid == 0) {
-        po->n_kp_qry = kp_count ? kp_count[slot_a0 + pair] : 0;
+        po->n_kp_qry = kp_count ? kp_count[slot_a0 + pair * stride_a] : 0;
         po->n_kp_ref = kp_count ? kp_count[slot_b0 + pair] : 0;
         po->n_matches = n;
         po->n_inliers = 0;
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(
 }
 
 int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, int ref_h, int ref_w, int do_tail,
-                  int min_matches, int use_kp_counts) {
+                  int min_matches, int use_kp_counts, int stride_a) {
     const int k = ctx->cfg.max_keypoints, iters = ctx->cfg.ransac_iters;
     GNB_CUDA(ctx, cudaMemsetAsync(ctx->range_flag, 0, sizeof(int) * pairs, ctx->stream));
     {
@@ -713,7 +713,7 @@ int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, in
     }
     GNB_KERNEL(ctx, "finalize_kernel", finalize_kernel<<<pairs, FIN_THREADS, 0, ctx->stream>>>(
         ctx->obj, ctx->mkp_qry, ctx->match_count, k, ctx->kmat, ctx->affine, iters, ctx->cfg.reproj_px,
-        min_matches, ctx->cfg.refine, ctx->hyp, ctx->hyp_count, ctx->range_flag, use_kp_counts ? ctx->kp_count : nullptr, 0,
+        min_matches, ctx->cfg.refine, ctx->hyp, ctx->hyp_count, ctx->range_flag, use_kp_counts ? ctx->kp_count : nullptr, 0, stride_a,
         ctx->cfg.max_batch, ref_h, ref_w, do_tail, ctx->inlier_mask, ctx->out_dev));
     return GNB_OK;
 }

@@ -141,6 +141,29 @@ class PoseEstimator:
                                                     C.c_void_p(affines.data_ptr()), 1, res))
         return [_from_c(x) for x in res]
 
+    def estimate_candidates(self, query: np.ndarray, tiles: np.ndarray, tile_ids, dems: Optional[np.ndarray], camera_info,
+                            affines: np.ndarray):
+        """Candidate search (BASELINE config 4): one query frame against n reference rasters whose
+        features are cached on the device by ``tile_ids`` (the reference caches the raster's features
+        per stamp, pose_node.py:226-241).  -> (index of the best candidate or None, results, cache hits)."""
+        query = np.ascontiguousarray(query, np.uint8)
+        tiles = np.ascontiguousarray(tiles, np.uint8)
+        n, ht, wt = tiles.shape
+        hq, wq = query.shape
+        k = _k9(camera_info)
+        affines = np.ascontiguousarray(np.asarray(affines, np.float64).reshape(n, 12))
+        ids = None if tile_ids is None else np.ascontiguousarray(np.asarray(tile_ids, np.int64).reshape(n))
+        if dems is not None:
+            dems = np.ascontiguousarray(dems, np.uint8).reshape(n, ht, wt)
+        res = (_lib.GnbPoseResult * n)()
+        hits = C.c_int(0)
+        self.ctx.check(self.ctx._lib.gnb_pose_candidates(self.ctx.handle, ptr(query), hq, wq, n, ptr(tiles), ht, wt, ptr(ids),
+                                                         ptr(dems), ptr(k), ptr(affines), res, C.byref(hits)))
+        out = [_from_c(x) for x in res]
+        ok = [i for i, r in enumerate(out) if r.ok]
+        best = max(ok, key=lambda i: out[i].n_inliers) if ok else None
+        return best, out, hits.value
+
     def estimate_from_images(self, query: np.ndarray, reference: np.ndarray, dem: Optional[np.ndarray], camera_info,
                              affine: np.ndarray) -> Optional[PoseResult]:
         res = self.estimate_batch(query[None], reference[None], None if dem is None else dem[None],

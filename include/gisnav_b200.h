@@ -68,6 +68,7 @@ typedef struct gnb_config {
     int32_t max_image_w;
     int32_t conv_impl;          /* 0 = tcgen05 implicit GEMM (product path); 1 = SIMT validation kernel */
     int32_t match_impl;         /* 0 = tcgen05 descriptor GEMM (product path); 1 = SIMT validation kernel */
+    int32_t tile_cache;         /* reference-raster feature cache entries (>= max_batch; pose_node.py:226-241) */
 } gnb_config;
 
 /* Fill cfg with the defaults listed above (K=1024, iters=2048, batch 8, 1088x1280 workspace). */
@@ -135,6 +136,17 @@ typedef struct gnb_pose_result {
 int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, int hq, int wq, const uint8_t* tiles,
                    int ht, int wt, const uint8_t* dems, const double* k9, const double* affine12,
                    int on_device, gnb_pose_result* results);
+
+/* Candidate search for ONE query frame (BASELINE.json config 4): the frame is extracted once and
+ * matched against n_tiles reference rasters (n_tiles <= max_batch).  Raster features are cached on
+ * the device keyed by tile_ids[i] (the reference re-extracts a raster only when its stamp changes,
+ * pose_node.py:226-241); id < 0 = never cached; tile_ids NULL = no caching.  tiles u8 [n,ht,wt],
+ * dems u8 [n,ht,wt] or NULL, k9 f64 [9], affine12 f64 [n,12].  results: HOST array of n_tiles;
+ * n_cache_hits (optional) = rasters whose features came from the cache. */
+int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* tiles, int ht,
+                        int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9, const double* affine12,
+                        gnb_pose_result* results, int* n_cache_hits);
+int gnb_cache_clear(gnb_ctx* ctx);
 
 /* ---- stage-isolated hooks (parity tests feed the oracle's intermediate into one stage) ------ */
 

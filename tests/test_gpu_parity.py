@@ -329,6 +329,39 @@ def test_batch_equals_single_and_is_deterministic():
     ctx.close()
 
 
+def test_candidate_search_with_tile_cache():
+    """Config-4 shape of work: one frame against several candidate rasters, raster features cached by id."""
+    blob = _trained_blob()
+    ground = synth.ground_texture(2048, seed=24, n_shapes=3000)
+    cfg = Config(max_batch=4, max_image_h=256, max_image_w=320, max_keypoints=512)
+    ctx = Context(cfg, weights=blob)
+    pe = PoseEstimator(ctx)
+    pairs = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256) for s in (1, 2)]
+    decoys = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256).tile for s in (11, 12, 13)]
+    tiles = np.stack([decoys[0], pairs[0].tile, decoys[1], decoys[2]])
+    ids = np.array([100, 101, 102, 103])
+    affines = np.stack([pairs[0].affine] * 4)
+    best, res, hits = pe.estimate_candidates(pairs[0].frame, tiles, ids, None, pairs[0].k, affines)
+    assert hits == 0 and best == 1, (best, [r.status for r in res])
+    single = pe.estimate_batch(pairs[0].frame[None], pairs[0].tile[None], None, pairs[0].k[None], pairs[0].affine[None])[0]
+    assert res[1].n_matches == single.n_matches and res[1].n_inliers == single.n_inliers
+    np.testing.assert_array_equal(res[1].r, single.r)
+    np.testing.assert_array_equal(res[1].ecef, single.ecef)
+    # same rasters again (all cached), different order and a new frame that belongs to none of them
+    order = [3, 1, 0, 2]
+    best2, res2, hits2 = pe.estimate_candidates(pairs[0].frame, tiles[order], ids[order], None, pairs[0].k, affines)
+    assert hits2 == 4 and best2 == 1
+    np.testing.assert_array_equal(res2[1].r, res[1].r)
+    assert [r.n_matches for r in res2] == [res[i].n_matches for i in order]
+    # one cached raster replaced by the second pair's own raster: only that one is extracted
+    tiles3 = tiles.copy(); tiles3[2] = pairs[1].tile
+    ids3 = ids.copy(); ids3[2] = 200
+    best3, res3, hits3 = pe.estimate_candidates(pairs[1].frame, tiles3, ids3, None, pairs[1].k, np.stack([pairs[1].affine] * 4))
+    assert hits3 == 3 and best3 == 2
+    assert np.abs(res3[2].camera_center - (-pairs[1].r_gt.T @ pairs[1].t_gt).ravel()).max() < 3.0
+    ctx.close()
+
+
 def test_full_size_properties():
     """BASELINE config 2 shape (1280x720 frame, 1024x1024 raster): size-independent properties."""
     blob = _trained_blob()
