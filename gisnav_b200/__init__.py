@@ -8,7 +8,7 @@ C ABI in ``include/gisnav_b200.h``.  There is no CPU fallback.
 from .context import Config, Context  # noqa: F401
 from .extractor import KeypointExtractor  # noqa: F401
 from .keypoint_record import KEYPOINT_DTYPE, KEYPOINT_DTYPE_256  # noqa: F401
-from .matcher import KeypointMatcher  # noqa: F401
+from .matcher import BruteForceRatioMatcher, KeypointMatcher  # noqa: F401
 from .pose import PoseEstimator, PoseResult, compute_pose  # noqa: F401
 
 __version__ = "0.1.0"

@@ -388,6 +388,40 @@ extern "C" int gnb_match(gnb_ctx* ctx, const float* desc_a, int n_a, const float
     return GNB_OK;
 }
 
+// TwistNode's matcher: brute-force 2-NN + ratio test (twist_node.py:248,263-267)
+extern "C" int gnb_knn_ratio_match(gnb_ctx* ctx, const float* desc_q, int n_q, const float* desc_r, int n_r, int dim, float ratio,
+                                   int64_t* out_idx, float* out_dist, int cap, int* n_out) {
+    if (!ctx || !n_out) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    *n_out = 0;
+    if (n_q == 0 || n_r < 2) return GNB_OK;   // knnMatch(k=2) yields no (m, n) pairs
+    if (!desc_q || !desc_r || dim < 1 || dim > 256) return GNB_E_INVALID;
+    const int k = ctx->cfg.max_keypoints;
+    if (n_q > k || n_r > k) { GNB_SET_ERR(ctx, "descriptor count exceeds max_keypoints=%d", k); return GNB_E_CAPACITY; }
+    if (ctx->cfg.match_impl != 0) { GNB_SET_ERR(ctx, "gnb_knn_ratio_match needs the tcgen05 matcher (match_impl = 0)"); return GNB_E_INVALID; }
+    int rc;
+    if ((rc = gnb_ensure_stage(ctx, (size_t)n_q * dim, (size_t)n_r * dim))) return rc;
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_a, desc_q, sizeof(float) * n_q * dim, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_b, desc_r, sizeof(float) * n_r * dim, cudaMemcpyHostToDevice, ctx->stream));
+    const int sb = ctx->cfg.max_batch;
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n_q, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count + sb, &n_r, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_SYNC(ctx);
+    if ((rc = gnb_knn_ratio(ctx, ctx->stage_a, n_q, ctx->stage_b, n_r, dim, (double)ratio))) return rc;
+    int n = 0;
+    if ((rc = read_count(ctx, ctx->match_count, &n))) return rc;
+    n = n < cap ? n : cap;
+    *n_out = n;
+    if (n > 0) {
+        std::vector<int> tmp(2 * n);
+        GNB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->match_idx, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_dist) GNB_CUDA(ctx, cudaMemcpyAsync(out_dist, ctx->match_score, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        GNB_SYNC(ctx);
+        if (out_idx) for (int i = 0; i < 2 * n; ++i) out_idx[i] = tmp[i];
+    }
+    return GNB_OK;
+}
+
 static void pairout_to_result(const PairOut& p, gnb_pose_result* r) {
     r->status = p.status; r->n_kp_qry = p.n_kp_qry; r->n_kp_ref = p.n_kp_ref; r->n_matches = p.n_matches;
     r->n_inliers = p.n_inliers; r->best_hypothesis = p.best_hypothesis;

@@ -175,6 +175,7 @@ int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots);
 // match slot_a[p] against slot_b[p] for p in [0, pairs): fills match_idx/score/count + mkp_*
 int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a = 1);
 int gnb_match_tc_init(gnb_ctx* ctx);
+int gnb_knn_ratio(gnb_ctx* ctx, const float* dq, int nq, const float* dr, int nr, int dim, double ratio);
 int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass);
 
 // pnp.cu

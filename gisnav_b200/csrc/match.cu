@@ -302,3 +302,68 @@ int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int strid
                                                    ctx->match_count, ctx->mkp_qry, ctx->mkp_ref));
     return GNB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// TwistNode's visual-odometry matcher (ros/gisnav/gisnav/core/twist_node.py:95,248,263-267):
+// cv2.BFMatcher().knnMatch(desc_qry, desc_ref, k=2) + Lowe ratio test m.distance < 0.7 n.distance.
+// The L2 distances come from the same tcgen05 descriptor GEMM as K4 (d^2 = |a|^2 + |b|^2 - 2 a.b).
+// SIFT descriptors are integers 0..255 stored as float: exactly representable in bf16 and every
+// partial sum is < 2^24, so d^2 is exact and the result is bit-identical to OpenCV's.
+__global__ void __launch_bounds__(256) knn_prepare_kernel(const float* __restrict__ desc, int n, int dim, int slot, int k_cap,
+                                                          bf16* __restrict__ out, float* __restrict__ norm2) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float ss = 0.f;
+    for (int c = lane; c < 256; c += 32) {
+        float v = c < dim ? desc[(size_t)row * dim + c] : 0.f;
+        const bf16 q = __float2bfloat16_rn(v);
+        out[((size_t)slot * k_cap + row) * 256 + c] = q;
+        const float qf = __bfloat162float(q);
+        ss = fmaf(qf, qf, ss);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if (lane == 0) norm2[(size_t)slot * k_cap + row] = ss;
+}
+
+__global__ void __launch_bounds__(1024) ratio_kernel(const float* __restrict__ d1sq, const float* __restrict__ d2sq,
+                                                     const int* __restrict__ j1, int n, double ratio, int* __restrict__ match_idx,
+                                                     float* __restrict__ match_dist, int* __restrict__ match_count) {
+    __shared__ int warp_sums[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        bool ok = false;
+        float dist1 = 0.f;
+        if (i < n) {
+            dist1 = sqrtf(fmaxf(d1sq[i], 0.f));
+            const float dist2 = sqrtf(fmaxf(d2sq[i], 0.f));
+            ok = (double)dist1 < ratio * (double)dist2;   // Python: m.distance < 0.7 * n.distance (float64 arithmetic)
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) warp_sums[wid] = __popc(ballot);
+        __syncthreads();
+        int offset = s_base;
+        for (int q = 0; q < wid; ++q) offset += warp_sums[q];
+        const int pos = offset + __popc(ballot & ((1u << lane) - 1));
+        if (ok) { match_idx[2 * pos] = i; match_idx[2 * pos + 1] = j1[i]; match_dist[pos] = dist1; }
+        __syncthreads();
+        if (threadIdx.x == 0) { int tot = 0; for (int q = 0; q < 32; ++q) tot += warp_sums[q]; s_base += tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) match_count[0] = s_base;
+}
+
+int gnb_knn_ratio(gnb_ctx* ctx, const float* dq, int nq, const float* dr, int nr, int dim, double ratio) {
+    const int k = ctx->cfg.max_keypoints, sb = ctx->cfg.max_batch;
+    GNB_KERNEL(ctx, "knn_prepare_kernel", knn_prepare_kernel<<<ceil_div(nq, 8), 256, 0, ctx->stream>>>(dq, nq, dim, 0, k, ctx->mproj, ctx->mlogit));
+    GNB_KERNEL(ctx, "knn_prepare_kernel", knn_prepare_kernel<<<ceil_div(nr, 8), 256, 0, ctx->stream>>>(dr, nr, dim, sb, k, ctx->mproj, ctx->mlogit));
+    int rc;
+    if ((rc = gnb_match_tc_rowpass(ctx, 1, 0, sb, 1, 2))) return rc;
+    GNB_KERNEL(ctx, "ratio_kernel", ratio_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->best_val, ctx->row_lse, ctx->best_idx, nq, ratio,
+                                                                              ctx->match_idx, ctx->match_score, ctx->match_count));
+    return GNB_OK;
+}

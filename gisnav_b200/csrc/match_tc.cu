@@ -177,13 +177,16 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
         int bi = -1;
         float rl = 0.f, la = 0.f;
         if (PASS == 1 && row < nr) { rl = row_lse[(size_t)rs_r * k_cap + row]; la = mlogit[(size_t)slot_r * k_cap + row]; }
+        if (PASS == 2 && row < nr) la = mlogit[(size_t)slot_r * k_cap + row];   // |a|^2
+        float b2v = INFINITY;   // PASS 2: second-smallest squared distance (bv = smallest, bi = its column)
+        if (PASS == 2) bv = INFINITY;
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j % MT_STAGES;
             const uint32_t ph = (j / MT_STAGES) & 1;
             const int c0 = j * MT_BN;
-            if (PASS == 1) {
+            if (PASS >= 1) {
                 const int col = c0 + et;
-                s_cl[s * MT_BN + et] = col < nc ? row_lse[(size_t)rs_c * k_cap + col] : 0.f;
+                s_cl[s * MT_BN + et] = (PASS == 1 && col < nc) ? row_lse[(size_t)rs_c * k_cap + col] : 0.f;
                 s_lb[s * MT_BN + et] = col < nc ? mlogit[(size_t)slot_c * k_cap + col] : 0.f;
                 tc::named_bar_sync(1, 128);
             }
@@ -207,6 +210,17 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
                         if (c0 + cc + i < nc) e += expf(__uint_as_float(v[i]) - nm);
                     run_sum = run_sum * expf(run_max - nm) + e;
                     run_max = nm;
+                } else if (PASS == 2) {
+                    // brute-force L2: d^2 = |a|^2 + |b|^2 - 2 a.b ; keep the two nearest (lowest index on ties)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c0 + cc + i;
+                        if (col < nc) {
+                            const float d2 = __fsub_rn(__fadd_rn(la, s_lb[s * MT_BN + cc + i]), __fmul_rn(2.0f, __uint_as_float(v[i])));
+                            if (d2 < bv) { b2v = bv; bv = d2; bi = col; }
+                            else if (d2 < b2v) b2v = d2;
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -230,6 +244,7 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
         if (row < nr) {
             if (PASS == 0) row_lse[(size_t)rs_r * k_cap + row] = run_max + logf(run_sum);
             else { best_val[(size_t)rs_r * k_cap + row] = bv; best_idx[(size_t)rs_r * k_cap + row] = bi; }
+            if (PASS == 2) row_lse[(size_t)rs_r * k_cap + row] = b2v;
         }
     }
     tc::tc_fence_before();
@@ -251,13 +266,17 @@ int gnb_match_tc_init(gnb_ctx* ctx) {
     if (rc) return rc;
     GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
     GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
+    GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
     return GNB_OK;
 }
 
 int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass) {
     const int k = ctx->cfg.max_keypoints;
-    dim3 grid(ceil_div(k, MT_BM), pairs, 2);
-    if (pass == 0)
+    dim3 grid(ceil_div(k, MT_BM), pairs, pass == 2 ? 1 : 2);
+    if (pass == 2)
+        GNB_KERNEL(ctx, "match_rows_tc<2>", match_rows_tc<2><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+    else if (pass == 0)
         GNB_KERNEL(ctx, "match_rows_tc<0>", match_rows_tc<0><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
             *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
     else

@@ -67,3 +67,28 @@ class KeypointMatcher:
             return sc[: n.value].reshape(-1, 1), idx[: n.value]
         dists, idx = self.match_arrays(desc1.detach().cpu().numpy(), desc2.detach().cpu().numpy())
         return torch.from_numpy(dists), torch.from_numpy(idx)
+
+
+class BruteForceRatioMatcher:
+    """Drop-in for TwistNode's matcher: ``self._bf = cv2.BFMatcher()`` ... ``knnMatch(desc_qry,
+    desc_ref, k=2)`` followed by the ratio test ``m.distance < CONFIDENCE_THRESHOLD * n.distance``
+    (ros/gisnav/gisnav/core/twist_node.py:54,95,248,263-267).  Returns the surviving (queryIdx,
+    trainIdx) pairs in query order and ``m.distance``."""
+
+    def __init__(self, ctx: Optional[Context] = None, ratio: float = 0.7, **ctx_kwargs):
+        self.ctx = ctx or Context(**ctx_kwargs)
+        self.ratio = ratio
+
+    def knn_ratio_match(self, desc_qry: np.ndarray, desc_ref: np.ndarray):
+        dq = np.ascontiguousarray(desc_qry, np.float32)
+        dr = np.ascontiguousarray(desc_ref, np.float32)
+        if dq.ndim != 2 or dr.ndim != 2 or (dq.size and dr.size and dq.shape[1] != dr.shape[1]):
+            raise ValueError("descriptors must be [N,D] with equal D")
+        dim = dq.shape[1] if dq.size else (dr.shape[1] if dr.size else 128)
+        cap = max(1, dq.shape[0])
+        idx = np.empty((cap, 2), np.int64)
+        dist = np.empty((cap,), np.float32)
+        n = C.c_int(0)
+        self.ctx.check(self.ctx._lib.gnb_knn_ratio_match(self.ctx.handle, ptr(dq), dq.shape[0], ptr(dr), dr.shape[0], dim,
+                                                         C.c_float(self.ratio), ptr(idx), ptr(dist), cap, C.byref(n)))
+        return idx[: n.value].copy(), dist[: n.value].copy()

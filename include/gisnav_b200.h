@@ -106,6 +106,14 @@ int gnb_extract(gnb_ctx* ctx, const uint8_t* image, int h, int w, int stride, in
 int gnb_match(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device,
               int64_t* out_idx, float* out_score, int cap, int* n_out);
 
+/* TwistNode's visual-odometry matcher — self._bf.knnMatch(desc_qry, desc_ref, k=2) + ratio test
+ * `m.distance < 0.7 * n.distance` (ros/gisnav/gisnav/core/twist_node.py:95,248,263-267).  desc f32
+ * [n,dim], dim <= 256 (SIFT: 128).  out_idx int64 [cap,2] (queryIdx, trainIdx) in query order,
+ * out_dist f32 [cap] = m.distance.  Exact (bit-identical to OpenCV) for integer-valued descriptors
+ * 0..255 such as SIFT's; bf16-rounded operands otherwise. */
+int gnb_knn_ratio_match(gnb_ctx* ctx, const float* desc_q, int n_q, const float* desc_r, int n_r, int dim, float ratio,
+                        int64_t* out_idx, float* out_dist, int cap, int* n_out);
+
 /* compute_pose: mkp_qry f32 [n,2], mkp_ref f32 [n,2], elevation u8 [dem_h,dem_w] (NULL => z=0),
  * k f64 [9] row-major -> r f64 [9] row-major, t f64 [3]; optional inlier mask u8 [n]. */
 int gnb_solve_pnp(gnb_ctx* ctx, const float* mkp_qry, const float* mkp_ref, int n, const uint8_t* dem,

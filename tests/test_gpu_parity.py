@@ -195,6 +195,47 @@ def test_k4_empty_and_golden(rand_blob, rand_params, stages):
     ctx.close()
 
 
+def test_twist_bf_ratio_matcher_bit_exact_vs_cv2(rand_blob):
+    """TwistNode's knnMatch(k=2) + ratio test on the tcgen05 GEMM, checked against
+    the reference's own cv2.BFMatcher call.  SIFT descriptors are integers 0..255 => exact distances."""
+    import cv2
+
+    from gisnav_b200 import BruteForceRatioMatcher
+    from oracle import bf_ref
+
+    ctx = _ctx(rand_blob, conv_impl=1, match_impl=0, max_keypoints=1024)
+    bf = BruteForceRatioMatcher(ctx)
+    g = synth.ground_texture(512, seed=31, n_shapes=400)
+    a, b = np.ascontiguousarray(g[40:296, 60:316]), np.ascontiguousarray(g[48:304, 70:326])
+    sift = cv2.SIFT_create(900)
+    ka, da = sift.detectAndCompute(a, None)
+    kb, db = sift.detectAndCompute(b, None)
+    da, db = da[:1024], db[:1024]
+    idx, dist = bf.knn_ratio_match(da, db)
+    idx_ref, dist_ref = bf_ref.knn_ratio_match(da, db)
+    np.testing.assert_array_equal(idx, idx_ref)
+    np.testing.assert_array_equal(dist, dist_ref)
+    assert len(idx) >= 30
+    # VO pose from the matches with a zero DEM, as twist_node.py:289 does
+    pq = np.array([ka[i].pt for i in idx[:, 0]], np.float32); pr = np.array([kb[j].pt for j in idx[:, 1]], np.float32)
+    k = np.array([[0.32 * 256, 0, 128], [0, 0.32 * 256, 128], [0, 0, 1.0]])
+    out = PoseEstimator(ctx).estimate(k, pq, pr, np.zeros_like(a))
+    assert out is not None
+    # ragged sizes, heavy ties (few distinct integer descriptors), degenerate inputs
+    rng = np.random.default_rng(4)
+    for n, m in ((37, 300), (513, 129), (5, 2)):
+        q = rng.integers(0, 4, (n, 128)).astype(np.float32) * 60
+        r = rng.integers(0, 4, (m, 128)).astype(np.float32) * 60
+        r[: min(n, m) // 2] = q[: min(n, m) // 2]
+        i1, d1 = bf.knn_ratio_match(q, r)
+        i2, d2 = bf_ref.knn_ratio_match(q, r)
+        np.testing.assert_array_equal(i1, i2)
+        np.testing.assert_array_equal(d1, d2)
+    e_idx, e_d = bf.knn_ratio_match(da[:10], db[:1])   # fewer than 2 train descriptors: no (m, n) pairs
+    assert e_idx.shape == (0, 2) and e_d.shape == (0,)
+    ctx.close()
+
+
 # ---- K5/K6: PnP + RANSAC + refit + tail ----------------------------------------------------------------
 @pytest.mark.parametrize("seed", range(5))
 def test_k5_ransac_bit_exact_and_pose(rand_blob, oracle, seed):

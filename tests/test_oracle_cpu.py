@@ -224,3 +224,30 @@ def test_stage_fixtures_reproduce(stages, rand_params):
     ms, idx = matcher_ref.match(stages["desc_a"], stages["desc_b"], rand_params, threshold=0.0)
     np.testing.assert_array_equal(idx, stages["match_idx_t0"])
     assert len(idx) > 10
+
+
+# ---- TwistNode matcher oracle = the reference's own cv2 calls ----------------------------------------
+def test_bf_ratio_oracle_on_sift():
+    import cv2
+
+    from oracle import bf_ref
+
+    g = synth.ground_texture(512, seed=31, n_shapes=400)
+    a, b = np.ascontiguousarray(g[40:296, 60:316]), np.ascontiguousarray(g[48:304, 70:326])
+    sift = cv2.SIFT_create(400)
+    ka, da = sift.detectAndCompute(a, None)
+    kb, db = sift.detectAndCompute(b, None)
+    assert da.dtype == np.float32 and np.all(da == np.round(da)) and da.max() <= 255  # integer-valued: exact in bf16
+    idx, dist = bf_ref.knn_ratio_match(da, db)
+    assert len(idx) >= 30  # MIN_MATCHES of TwistNode (twist_node.py:57)
+    pa = np.array([ka[i].pt for i in idx[:, 0]]); pb = np.array([kb[j].pt for j in idx[:, 1]])
+    shift = np.median(pa - pb, axis=0)
+    assert np.abs(shift - np.array([10.0, 8.0])).max() < 1.0  # the views are offset by (10, 8) px
+    # brute-force restatement of knnMatch + ratio in numpy (exact for integer descriptors)
+    d2 = (da.astype(np.float64) ** 2).sum(1)[:, None] + (db.astype(np.float64) ** 2).sum(1)[None] - 2 * da.astype(np.float64) @ db.astype(np.float64).T
+    order = np.argsort(d2, axis=1, kind="stable")[:, :2]
+    d1 = np.sqrt(d2[np.arange(len(da)), order[:, 0]].astype(np.float32)); dd2 = np.sqrt(d2[np.arange(len(da)), order[:, 1]].astype(np.float32))
+    keep = d1.astype(np.float64) < 0.7 * dd2.astype(np.float64)
+    np.testing.assert_array_equal(idx[:, 0], np.nonzero(keep)[0])
+    np.testing.assert_array_equal(idx[:, 1], order[keep, 0])
+    np.testing.assert_array_equal(dist, d1[keep])
