@@ -164,6 +164,14 @@ class PoseEstimator:
         best = max(ok, key=lambda i: out[i].n_inliers) if ok else None
         return best, out, hits.value
 
+    def estimate_from_message(self, query: np.ndarray, reference: np.ndarray, dem: Optional[np.ndarray], camera_info,
+                              crs: str) -> Optional[PoseResult]:
+        """Fields of an ``OrthoStereoImage`` message (ros/gisnav_msgs/msg/OrthoStereoImage.msg:14-18) as
+        PoseNode receives them: mono8 query / reference / dem arrays and the ``+proj=affine`` CRS string."""
+        from .crs import proj_to_affine
+
+        return self.estimate_from_images(query, reference, dem, camera_info, proj_to_affine(crs))
+
     def estimate_from_images(self, query: np.ndarray, reference: np.ndarray, dem: Optional[np.ndarray], camera_info,
                              affine: np.ndarray) -> Optional[PoseResult]:
         res = self.estimate_batch(query[None], reference[None], None if dem is None else dem[None],

@@ -140,3 +140,16 @@ def test_two_process_gloo_broadcast_and_sharding(tmp_path):
         assert dig[1] == str(r) and dig[2] == want
     line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT")][0].split()
     assert (int(line[1]), int(line[2])) == (9, 36)  # 9 pairs processed exactly once across 2 ranks
+
+
+def test_crs_string_ingest_matches_reference_parser():
+    from gisnav_b200 import crs, synth
+    from oracle import tail_ref
+
+    a = synth.tile_affine(1234.0, 567.0)
+    s_ref = tail_ref.affine_to_proj(a)  # restatement of _transformations.py:274-298
+    np.testing.assert_array_equal(crs.proj_to_affine(s_ref), tail_ref.proj_to_affine(s_ref))
+    np.testing.assert_array_equal(crs.proj_to_affine(crs.affine_to_proj(a)), a)
+    np.testing.assert_array_equal(tail_ref.proj_to_affine(crs.affine_to_proj(a)), a)
+    with pytest.raises(ValueError):
+        crs.proj_to_affine("+proj=affine +xoff=1")
