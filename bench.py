@@ -331,19 +331,38 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
-        # dominant kernel family = the dense conv stack (K1)
-        conv_names = [k for k in prof if k.startswith("conv")]
-        conv_ms = sum(prof[k][0] for k in conv_names)
-        conv_launches = sum(prof[k][1] for k in conv_names)
-        flop_per_step = FLOP_PER_PIXEL * args.batch * (FRAME_HW[0] * FRAME_HW[1] + TILE * TILE)
-        achieved = flop_per_step * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+        # dominant kernel = the fused conv1a+conv1b+pool launch (K1's full-resolution block): 37 440 MAC per
+        # input pixel (576 + 36 864); two launches per step (frames, rasters)
+        px_step = args.batch * (FRAME_HW[0] * FRAME_HW[1] + TILE * TILE)
+        dom = "conv_tc:1a+1b" if "conv_tc:1a+1b" in prof else max((k for k in prof if k.startswith("conv")), key=lambda k: prof[k][0])
+        dom_ms, dom_launches = prof[dom]
+        dom_flop_step = 2.0 * 37440.0 * px_step if dom == "conv_tc:1a+1b" else None
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        achieved = dom_flop_step * args.steps / (dom_ms * 1e-3) / 1e12 if dom_flop_step else None
+        traffic = None
+        try:  # dram bytes per launch from the committed `ncu --set full` capture (batch 16), scaled to this batch
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_step_batch16.json")))
+            rows = [r for r in cap if r["kernel"].startswith("conv1_fused_kernel")]
+            if rows and dom == "conv_tc:1a+1b":
+                traffic = sum(r["dram_read_mb"] + r["dram_write_mb"] for r in rows) / len(rows) * 1e6 * args.batch / 16.0
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {
-            "bound": "tensor", "kernel": "K1 conv stack (all conv* launches)", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+            "bound": "tensor", "kernel": f"{dom} (conv1_fused_kernel: im2col -> tcgen05 conv1a -> TMEM -> tcgen05 conv1b -> pool)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+            "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r01_ncu_full_step_batch16.json)",
+            "algorithmic_flop_per_launch": dom_flop_step / 2.0 if dom_flop_step else None,
+            "algorithmic_bytes_per_launch": px_step / 2.0 * (1 + 32) if dom_flop_step else None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
-            "launches_timed": conv_launches, "kernel_ms_total": conv_ms, "share_of_step": conv_ms / ms if ms > 0 else None,
+            "launches_timed": dom_launches, "kernel_ms_total": dom_ms, "share_of_step": dom_ms / ms if ms > 0 else None,
         }
+        # the whole dense stack (all conv*/head launches) against the same peak, for context
+        conv_names = [k for k in prof if k.startswith("conv") or k in ("score_head_tc", "desc_head_tc")]
+        conv_ms = sum(prof[k][0] for k in conv_names)
+        stack_flop = FLOP_PER_PIXEL * px_step
+        roofline_stack = {"kernel": "K1 dense stack (all conv*/head launches)", "achieved": stack_flop * args.steps / (conv_ms * 1e-3) / 1e12,
+                          "peak": peak, "unit": "TFLOP/s", "frac": stack_flop * args.steps / (conv_ms * 1e-3) / 1e12 / peak,
+                          "kernel_ms_total": conv_ms, "share_of_step": conv_ms / ms if ms > 0 else None}
         frame_b = FRAME_HW[0] * FRAME_HW[1]
         h2d = args.batch * (frame_b + 2 * TILE * TILE + 9 * 8 + 12 * 8)
         d2h = args.batch * 200
@@ -355,7 +374,7 @@ def run_b200(args):
             "e2e": {"value": matched_e2e_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_all),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "roofline_stack": roofline_stack, "cpu_baseline": cpu_baseline,
             "matched_fraction": matched_all / total_all if total_all else None,
             "pairs_per_sec_processed": total_all / (ms * 1e-3),
             "pose_rmse_px_vs_ground_truth": float(np.sqrt(np.mean(np.square(err_gt)))) if err_gt else None,
