@@ -199,6 +199,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
+    gnb_tc_state_free(ctx);
     delete[] ctx->cache_ids;
     delete[] ctx->cache_lru;
     if (ctx->prof) {

@@ -56,6 +56,7 @@ struct gnb_ctx {
     ConvLayer layers[GNB_NUM_LAYERS];
     // matcher head
     bf16* match_w;    // [256 out][256 in]
+    bf16* match_wt;   // [256 in][256 out] transposed copy for the SIMT projection
     float* match_b;   // [256]
     bf16* match_mw;   // [256]
     float match_mb;
@@ -104,6 +105,7 @@ struct gnb_ctx {
     int* c_kp_count;                // [cache_cap]
     bf16* c_mproj;                  // [cache_cap][K][256]
     float* c_mlogit;                // [cache_cap][K]
+    void* tc_state;                 // TcState* (tc_common.cuh): tensor maps bound to this context's buffers
     // profiling
     int prof_on;
     void* prof;  // ProfState*
@@ -175,6 +177,7 @@ int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots);
 // match slot_a[p] against slot_b[p] for p in [0, pairs): fills match_idx/score/count + mkp_*
 int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a = 1);
 int gnb_match_tc_init(gnb_ctx* ctx);
+void gnb_tc_state_free(gnb_ctx* ctx);
 int gnb_knn_ratio(gnb_ctx* ctx, const float* dq, int nq, const float* dr, int nr, int dim, double ratio);
 int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass);
 

@@ -13,7 +13,7 @@
 #include <vector>
 
 struct CUtensorMap_st;
-const CUtensorMap_st* gnb_conv_tc_wmap(int lid);
+const CUtensorMap_st* gnb_conv_tc_wmap(gnb_ctx* ctx, int lid);
 int gnb_score_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* apa, const float* bias, int n, int hc, int wc, float* score);
 int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out_p1);
 int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0);
@@ -312,7 +312,7 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
     const int cells = n * (h / 8) * (w / 8);
     if (ctx->cfg.conv_impl == 0) {
         // detector head fused: 1x1 conv + softmax + depth-to-space straight into the score map
-        if ((rc = gnb_score_head_tc(ctx, gnb_conv_tc_wmap(LPB), cw.apa, ctx->layers[LPB].bias, n, h / 8, w / 8, cw.score))) return rc;
+        if ((rc = gnb_score_head_tc(ctx, gnb_conv_tc_wmap(ctx, LPB), cw.apa, ctx->layers[LPB].bias, n, h / 8, w / 8, cw.score))) return rc;
     } else {
         if ((rc = conv_layer(ctx, LPB, cw.apa, n, h / 8, w / 8, nullptr, cw.semi, 0, 0))) return rc;
         GNB_KERNEL(ctx, "softmax_d2s_kernel", softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score));
@@ -328,6 +328,6 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
 
 int gnb_describe(gnb_ctx* ctx, int n, int h, int w, int slot0) {
     if (ctx->cfg.conv_impl == 0)
-        return gnb_desc_head_tc(ctx, gnb_conv_tc_wmap(LDB), ctx->cw.ada, ctx->layers[LDB].bias, n, h, w, slot0);
+        return gnb_desc_head_tc(ctx, gnb_conv_tc_wmap(ctx, LDB), ctx->cw.ada, ctx->layers[LDB].bias, n, h, w, slot0);
     return gnb_kp_sample(ctx, ctx->cw.dense, n, h, w, slot0);
 }

@@ -19,8 +19,6 @@
 
 int* gnb_tc_err_dev(gnb_ctx* ctx);
 
-struct ConvTcLayerMaps { CUtensorMap w; CUtensorMap w64; CUtensorMap w128; int valid; };
-static ConvTcLayerMaps g_wmaps[GNB_NUM_LAYERS];
 
 template <int NPAD>
 __global__ void __launch_bounds__(256) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in,
@@ -682,7 +680,7 @@ int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf
     const int total = ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n;
     const int grid = total < ctx->sm_count ? total : ctx->sm_count;
     GNB_KERNEL(ctx, "conv_tc:1a+1b", conv1_fused_kernel<<<grid, F1_THREADS, F1_SMEM, ctx->stream>>>(
-        timg, ctx->layers[L1A].w, ctx->layers[L1A].bias, g_wmaps[L1B].w64, ctx->layers[L1B].bias, h, w, n, out_p1, gnb_tc_err_dev(ctx)));
+        timg, ctx->layers[L1A].w, ctx->layers[L1A].bias, tc_state(ctx)->layers[L1B].w64, ctx->layers[L1B].bias, h, w, n, out_p1, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
 
@@ -701,10 +699,14 @@ static int launch_conv_tc(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMa
     return GNB_OK;
 }
 
-const CUtensorMap* gnb_conv_tc_wmap(int lid) { return g_wmaps[lid].valid ? &g_wmaps[lid].w : nullptr; }
+const CUtensorMap* gnb_conv_tc_wmap(gnb_ctx* ctx, int lid) {
+    TcLayerMaps& m = tc_state(ctx)->layers[lid];
+    return m.valid ? &m.w : nullptr;
+}
 
 int gnb_conv_tc_init(gnb_ctx* ctx) {
     if (!gnb_tc_err_dev(ctx)) { GNB_SET_ERR(ctx, "cannot allocate the host-mapped error word"); return GNB_E_CUDA; }
+    TcLayerMaps* g_wmaps = tc_state(ctx)->layers;
     for (int l = 0; l < GNB_NUM_LAYERS; ++l) {
         const ConvLayer& L = ctx->layers[l];
         g_wmaps[l].valid = 0;
@@ -728,6 +730,7 @@ int gnb_conv_tc_init(gnb_ctx* ctx) {
 int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, int h, int w, bf16* out_bf, float* out_f,
                       int relu, int pool) {
     const int lid = (int)(&L - ctx->layers);
+    TcLayerMaps* g_wmaps = tc_state(ctx)->layers;
     if (lid < 0 || lid >= GNB_NUM_LAYERS || !g_wmaps[lid].valid) return GNB_E_INVALID;
     if (pool && ((h | w) & 1)) return GNB_E_INVALID;
     static const char* kNames[GNB_NUM_LAYERS] = {"conv1a", "conv_tc:1b", "conv_tc:2a", "conv_tc:2b", "conv_tc:3a", "conv_tc:3b",

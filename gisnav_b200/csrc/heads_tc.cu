@@ -341,3 +341,146 @@ int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap* tmap_w, const bf16* ada, c
         *tmap_w, ada, bias, h / 8, w / 8, h, w, ctx->kp_xy, ctx->kp_count, slot0, k, ctx->desc_f32, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// LightGlue final projection on tcgen05: m = (W d + b) / 256^(1/4) for 128 keypoints per CTA, plus
+// the matchability logit z = w_m . d + b_m as a second, 16-column MMA on the same A operand
+// (B2 = [w_m; 0 ...]).  A = bf16(descriptors) gathered row-wise into the 128B-swizzle layout.
+#define PJ_W2_BYTES (4 * 16 * 128)   // four K chunks of [16 rows x 128 B]; row 0 = w_m
+#define PJ_SMEM (1024 + DH_W_BYTES + PJ_W2_BYTES + DH_A_BYTES + 256 + 256 * 4)
+
+__global__ void __launch_bounds__(256, 1) project_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ desc,
+                                                            const int* __restrict__ kp_count, int slot0, int k_cap,
+                                                            const float* __restrict__ bias, const bf16* __restrict__ mw, float mb,
+                                                            bf16* __restrict__ mproj, float* __restrict__ mlogit, int* err) {
+    const int slot = slot0 + blockIdx.y;
+    const int n_kp = max(kp_count[slot], 0);
+    const int kp0 = blockIdx.x * 128;
+    if (kp0 >= n_kp) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;
+    uint8_t* sW2 = sW + DH_W_BYTES;
+    uint8_t* sA = sW2 + PJ_W2_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + DH_A_BYTES);
+    uint64_t* w_full = bars;
+    uint64_t* acc_full = bars + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_w);
+        tc::mbar_init(w_full, 1);
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+    s_bias[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    if (warp == 0 && lane == 0) {
+        tc::mbar_arrive_expect_tx(w_full, DH_W_BYTES);
+        for (int c = 0; c < 4; ++c) tc::tma_load_3d(sW + c * 256 * 128, &tmap_w, w_full, c * 64, 0, 0);
+    }
+    // B2: row 0 = w_m (bf16), rows 1..15 = 0
+    for (int item = threadIdx.x; item < 4 * 16 * 8; item += 256) {
+        const int chunk = item >> 7, row = (item >> 3) & 15, j = item & 7;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (row == 0) val = *reinterpret_cast<const uint4*>(mw + chunk * 64 + j * 8);
+        *reinterpret_cast<uint4*>(sW2 + chunk * 16 * 128 + row * 128 + ((j ^ (row & 7)) << 4)) = val;
+    }
+    // A: 128 keypoints x 256 ch, f32 -> bf16; item = (row, group of 8 channels)
+    const float* dbase = desc + ((size_t)slot * k_cap + kp0) * 256;
+    for (int item = threadIdx.x; item < 128 * 32; item += 256) {
+        const int m = item >> 5, piece = item & 31;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (kp0 + m < n_kp) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(dbase + (size_t)m * 256 + piece * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(dbase + (size_t)m * 256 + piece * 8 + 4));
+            val = make_uint4(tc::pack_bf16x2(a.x, a.y), tc::pack_bf16x2(a.z, a.w), tc::pack_bf16x2(b.x, b.y), tc::pack_bf16x2(b.z, b.w));
+        }
+        const int chunk = piece >> 3, j = piece & 7;
+        *reinterpret_cast<uint4*>(sA + chunk * 128 * 128 + m * 128 + ((j ^ (m & 7)) << 4)) = val;
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) {
+        const bool ok = tc::mbar_wait(w_full, 0, err, 321);
+        if (ok && tc::elect_one()) {
+            const uint32_t idesc = tc::make_idesc_bf16(128, 256), idesc2 = tc::make_idesc_bf16(128, 16);
+            const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA), 1024);
+            const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
+            const uint64_t db2 = tc::make_smem_desc_sw128(tc::smem_u32(sW2), 1024);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t da = da0 + (uint64_t)((c * 128 * 128 + k * 32) >> 4);
+                    tc::umma_bf16(tmem_base, da, db0 + (uint64_t)((c * 256 * 128 + k * 32) >> 4), idesc, (c | k) ? 1u : 0u);
+                    tc::umma_bf16(tmem_base + 256u, da, db2 + (uint64_t)((c * 16 * 128 + k * 32) >> 4), idesc2, (c | k) ? 1u : 0u);
+                }
+            tc::umma_commit(acc_full);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp & 3, m = q * 32 + lane, kp = kp0 + m;
+        const bool ok = tc::mbar_wait(acc_full, 0, err, 322);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (ok) {
+            bf16* o = mproj + ((size_t)slot * k_cap + kp) * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + c0, r);
+                tc::tmem_ld_wait();
+                if (kp < n_kp) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = c0 + g * 8 + 2 * j;
+                            pk[j] = tc::pack_bf16x2(__fmul_rn(__fadd_rn(__uint_as_float(r[g * 8 + 2 * j]), s_bias[c]), 0.25f),
+                                                    __fmul_rn(__fadd_rn(__uint_as_float(r[g * 8 + 2 * j + 1]), s_bias[c + 1]), 0.25f));
+                        }
+                        *reinterpret_cast<uint4*>(o + c0 + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+            uint32_t r[32];
+            tc::tmem_ld32(taddr + 256u, r);
+            tc::tmem_ld_wait();
+            if (kp < n_kp) {
+                const float z = __uint_as_float(r[0]) + mb;
+                mlogit[(size_t)slot * k_cap + kp] = fminf(z, 0.f) - log1pf(expf(-fabsf(z)));
+            }
+        }
+        tc::tc_fence_before();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+int gnb_project_tc(gnb_ctx* ctx, int slot0, int n_slots) {
+    TcState* ts = tc_state(ctx);
+    CUtensorMap& g_proj_wmap = ts->proj_map;
+    if (!ts->proj_ready) {
+        const uint64_t dims[3] = {256, 256, 1};
+        const uint64_t strides[2] = {512, 256 * 512};
+        const uint32_t box[3] = {64, 256, 1};
+        int rc = gnb_make_tmap_bf16(ctx, &g_proj_wmap, ctx->match_w, 3, dims, strides, box);
+        if (rc) return rc;
+        GNB_CUDA(ctx, cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM));
+        ts->proj_ready = 1;
+    }
+    const int k = ctx->cfg.max_keypoints;
+    dim3 grid(ceil_div(k, 128), n_slots);
+    GNB_KERNEL(ctx, "project_tc", project_tc_kernel<<<grid, 256, PJ_SMEM, ctx->stream>>>(
+        g_proj_wmap, ctx->desc_f32, ctx->kp_count, slot0, k, ctx->match_b, ctx->match_mw, ctx->match_mb, ctx->mproj, ctx->mlogit,
+        gnb_tc_err_dev(ctx)));
+    return GNB_OK;
+}

@@ -23,7 +23,6 @@ static inline uint16_t f2bf_bits(float f) {
     return (uint16_t)(u >> 16);
 }
 
-static bf16* g_match_wt = nullptr;  // [256 in][256 out] transposed copy for the SIMT projection
 
 int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const float* m_w, float m_b) {
     std::vector<uint16_t> w(256 * 256), wt(256 * 256), mw(256);
@@ -34,11 +33,11 @@ int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const
         }
     for (int i = 0; i < 256; ++i) mw[i] = f2bf_bits(m_w[i]);
     GNB_CUDA(ctx, cudaMalloc(&ctx->match_w, 256 * 256 * 2));
-    GNB_CUDA(ctx, cudaMalloc(&g_match_wt, 256 * 256 * 2));
+    GNB_CUDA(ctx, cudaMalloc(&ctx->match_wt, 256 * 256 * 2));
     GNB_CUDA(ctx, cudaMalloc(&ctx->match_b, 256 * 4));
     GNB_CUDA(ctx, cudaMalloc(&ctx->match_mw, 256 * 2));
     GNB_CUDA(ctx, cudaMemcpy(ctx->match_w, w.data(), 256 * 256 * 2, cudaMemcpyHostToDevice));
-    GNB_CUDA(ctx, cudaMemcpy(g_match_wt, wt.data(), 256 * 256 * 2, cudaMemcpyHostToDevice));
+    GNB_CUDA(ctx, cudaMemcpy(ctx->match_wt, wt.data(), 256 * 256 * 2, cudaMemcpyHostToDevice));
     GNB_CUDA(ctx, cudaMemcpy(ctx->match_b, proj_b, 256 * 4, cudaMemcpyHostToDevice));
     GNB_CUDA(ctx, cudaMemcpy(ctx->match_mw, mw.data(), 256 * 2, cudaMemcpyHostToDevice));
     ctx->match_mb = m_b;
@@ -49,7 +48,7 @@ void gnb_match_free(gnb_ctx* ctx) {
     if (ctx->match_w) cudaFree(ctx->match_w);
     if (ctx->match_b) cudaFree(ctx->match_b);
     if (ctx->match_mw) cudaFree(ctx->match_mw);
-    if (g_match_wt) { cudaFree(g_match_wt); g_match_wt = nullptr; }
+    if (ctx->match_wt) { cudaFree(ctx->match_wt); ctx->match_wt = nullptr; }
     ctx->match_w = nullptr; ctx->match_b = nullptr; ctx->match_mw = nullptr;
 }
 
@@ -96,10 +95,13 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
     }
 }
 
+int gnb_project_tc(gnb_ctx* ctx, int slot0, int n_slots);
+
 int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots) {
+    if (ctx->cfg.match_impl == 0) return gnb_project_tc(ctx, slot0, n_slots);
     const int k = ctx->cfg.max_keypoints;
     dim3 grid(ceil_div(k, 8), n_slots);
-    GNB_KERNEL(ctx, "project_kernel", project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->desc_f32, ctx->kp_count, slot0, k, g_match_wt, ctx->match_b,
+    GNB_KERNEL(ctx, "project_kernel", project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->desc_f32, ctx->kp_count, slot0, k, ctx->match_wt, ctx->match_b,
                                                   ctx->match_mw, ctx->match_mb, ctx->mproj, ctx->mlogit));
     return GNB_OK;
 }

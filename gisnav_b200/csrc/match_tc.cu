@@ -23,7 +23,6 @@
 #define MT_TMEM_COLS 256   // 2 accumulator stages x 128 columns
 #define MT_SMEM_BYTES (1024 + MT_TILE_BYTES * (1 + MT_STAGES) + 256 + 2 * 2 * MT_BN * 4)
 
-static CUtensorMap* g_tmap_host = nullptr;   // pinned copy kept for the kernel parameter
 static int* g_tc_err_host = nullptr;         // host-mapped error word written by timed-out waits
 static int* g_tc_err_dev = nullptr;
 
@@ -56,6 +55,10 @@ int gnb_make_tmap_bf16(gnb_ctx* ctx, CUtensorMap* out, void* base, int rank, con
         return GNB_E_CUDA;
     }
     return GNB_OK;
+}
+
+void gnb_tc_state_free(gnb_ctx* ctx) {
+    if (ctx->tc_state) { delete static_cast<TcState*>(ctx->tc_state); ctx->tc_state = nullptr; }
 }
 
 int* gnb_tc_err_dev(gnb_ctx* ctx) {
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
 
 int gnb_match_tc_init(gnb_ctx* ctx) {
     if (!gnb_tc_err_dev(ctx)) { GNB_SET_ERR(ctx, "cannot allocate the host-mapped error word"); return GNB_E_CUDA; }
-    if (!g_tmap_host) g_tmap_host = new CUtensorMap();
+    CUtensorMap* g_tmap_host = &tc_state(ctx)->match_map;
     const uint64_t k = (uint64_t)ctx->cfg.max_keypoints;
     const uint64_t dims[3] = {MT_K, k, (uint64_t)ctx->kp_slots};
     const uint64_t strides[2] = {MT_K * 2, k * MT_K * 2};
@@ -272,6 +275,7 @@ int gnb_match_tc_init(gnb_ctx* ctx) {
 
 int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass) {
     const int k = ctx->cfg.max_keypoints;
+    CUtensorMap* g_tmap_host = &tc_state(ctx)->match_map;
     dim3 grid(ceil_div(k, MT_BM), pairs, pass == 2 ? 1 : 2);
     if (pass == 2)
         GNB_KERNEL(ctx, "match_rows_tc<2>", match_rows_tc<2><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(

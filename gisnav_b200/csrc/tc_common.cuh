@@ -154,6 +154,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 
 }  // namespace tc
 
+// ---- per-context tensor maps (they embed device pointers of THIS context's buffers) -----------------
+struct TcLayerMaps { CUtensorMap w; CUtensorMap w64; CUtensorMap w128; int valid; };
+struct TcState {
+    TcLayerMaps layers[GNB_NUM_LAYERS];
+    CUtensorMap match_map;   // mproj [slots][K][256]
+    CUtensorMap proj_map;    // match head projection weights [256][256]
+    int proj_ready;
+};
+static inline TcState* tc_state(gnb_ctx* ctx) {
+    if (!ctx->tc_state) ctx->tc_state = new TcState();
+    return static_cast<TcState*>(ctx->tc_state);
+}
+
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ---
 typedef CUresult (*gnb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

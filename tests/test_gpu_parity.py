@@ -370,6 +370,28 @@ def test_batch_equals_single_and_is_deterministic():
     ctx.close()
 
 
+def test_two_live_contexts_do_not_share_state(rand_blob):
+    """Tensor maps, repacked weights and workspaces belong to a context: two contexts with different
+    weights used alternately must each reproduce their own single-context result."""
+    blob_b = W.pack(W.random_init(1))
+    img = np.ascontiguousarray(synth.ground_texture(512, seed=13, n_shapes=300)[0:96, 0:128])
+    ref = []
+    for blob in (rand_blob, blob_b):
+        c = _ctx(blob, max_keypoints=128)
+        ref.append(KeypointExtractor(c).detect_and_compute_arrays(img))
+        c.close()
+    ca, cb = _ctx(rand_blob, max_keypoints=128), _ctx(blob_b, max_keypoints=128)
+    for _ in range(2):
+        for c, want in ((ca, ref[0]), (cb, ref[1])):
+            xy, sc, desc = KeypointExtractor(c).detect_and_compute_arrays(img)
+            np.testing.assert_array_equal(xy, want[0])
+            np.testing.assert_array_equal(desc, want[2])
+            s1, i1 = KeypointMatcher(c).match_arrays(desc, desc[::-1].copy())
+            assert len(i1) > 0 and np.all(i1[:, 0] + i1[:, 1] == len(desc) - 1)   # self-match through the reversal
+    assert not np.array_equal(ref[0][2][: min(len(ref[0][2]), len(ref[1][2]))], ref[1][2][: min(len(ref[0][2]), len(ref[1][2]))])
+    ca.close(); cb.close()
+
+
 def test_candidate_search_with_tile_cache():
     """Config-4 shape of work: one frame against several candidate rasters, raster features cached by id."""
     blob = _trained_blob()
