@@ -21,7 +21,9 @@
 #define MT_TILE_BYTES (MT_CHUNK_BYTES * (MT_K / MT_KC))  // 64 KB: one operand tile, full K
 #define MT_STAGES 2
 #define MT_TMEM_COLS 256   // 2 accumulator stages x 128 columns
-#define MT_SMEM_BYTES (1024 + MT_TILE_BYTES * (1 + MT_STAGES) + 256 + 2 * 2 * MT_BN * 4)
+#define MT_EPI_GROUPS 2     // epilogue warpgroups: group g consumes columns [64 g, 64 g + 64) of every tile
+#define MT_THREADS (128 + 128 * MT_EPI_GROUPS)
+#define MT_SMEM_BYTES (1024 + MT_TILE_BYTES * (1 + MT_STAGES) + 256 + 2 * 2 * MT_BN * 4 + 3 * 128 * 4)
 
 static int* g_tc_err_host = nullptr;         // host-mapped error word written by timed-out waits
 static int* g_tc_err_dev = nullptr;
@@ -80,7 +82,7 @@ int gnb_tc_err_check(gnb_ctx* ctx) {
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mlogit,
+__global__ void __launch_bounds__(MT_THREADS, 1) match_rows_tc(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mlogit,
                                                         const int* __restrict__ kp_count, int k_cap, int slot_a0, int stride_a, int slot_b0, int max_pairs,
                                                         float* __restrict__ row_lse, float* __restrict__ best_val,
                                                         int* __restrict__ best_idx, int* err) {
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     float* s_cl = reinterpret_cast<float*>(smem + MT_TILE_BYTES * (1 + MT_STAGES) + 256);  // [2][128] column LSE
     float* s_lb = s_cl + 2 * MT_BN;                                                       // [2][128] column logit
+    float* s_mrg = s_lb + 2 * MT_BN;                                                      // [3][128] partials of epilogue group 1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
             tc::mbar_init(&b_full[s], 1);
             tc::mbar_init(&b_empty[s], 1);
             tc::mbar_init(&t_full[s], 1);
-            tc::mbar_init(&t_empty[s], 4);  // one arrive per epilogue warp
+            tc::mbar_init(&t_empty[s], 4 * MT_EPI_GROUPS);  // one arrive per epilogue warp
         }
         tc::fence_barrier_init();
     }
@@ -175,7 +178,8 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_local = q * 32 + lane;
         const int row = r0 + row_local;
-        const int et = threadIdx.x - 128;       // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 128;       // 0..255 among the epilogue threads
+        const int grp = et >> 7;                // which half of each tile's columns this thread consumes
         float run_max = -INFINITY, run_sum = 0.f, bv = -INFINITY;
         int bi = -1;
         float rl = 0.f, la = 0.f;
@@ -188,16 +192,18 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
             const uint32_t ph = (j / MT_STAGES) & 1;
             const int c0 = j * MT_BN;
             if (PASS >= 1) {
-                const int col = c0 + et;
-                s_cl[s * MT_BN + et] = (PASS == 1 && col < nc) ? row_lse[(size_t)rs_c * k_cap + col] : 0.f;
-                s_lb[s * MT_BN + et] = col < nc ? mlogit[(size_t)slot_c * k_cap + col] : 0.f;
-                tc::named_bar_sync(1, 128);
+                if (et < MT_BN) {
+                    const int col = c0 + et;
+                    s_cl[s * MT_BN + et] = (PASS == 1 && col < nc) ? row_lse[(size_t)rs_c * k_cap + col] : 0.f;
+                    s_lb[s * MT_BN + et] = col < nc ? mlogit[(size_t)slot_c * k_cap + col] : 0.f;
+                }
+                tc::named_bar_sync(1, 128 * MT_EPI_GROUPS);
             }
             if (!tc::mbar_wait(&t_full[s], ph, err, 105)) break;
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * MT_BN);
 #pragma unroll 1
-            for (int cc = 0; cc < MT_BN; cc += 32) {
+            for (int cc = grp * (MT_BN / MT_EPI_GROUPS); cc < (grp + 1) * (MT_BN / MT_EPI_GROUPS); cc += 32) {
                 uint32_t v[32];
                 tc::tmem_ld32(taddr + cc, v);
                 tc::tmem_ld_wait();
@@ -206,13 +212,15 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (c0 + cc + i < nc) m = fmaxf(m, __uint_as_float(v[i]));
-                    const float nm = fmaxf(run_max, m);
-                    float e = 0.f;
+                    if (m > -INFINITY) {   // a chunk made only of masked columns leaves the running pair untouched
+                        const float nm = fmaxf(run_max, m);
+                        float e = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c0 + cc + i < nc) e += expf(__uint_as_float(v[i]) - nm);
-                    run_sum = run_sum * expf(run_max - nm) + e;
-                    run_max = nm;
+                        for (int i = 0; i < 32; ++i)
+                            if (c0 + cc + i < nc) e += expf(__uint_as_float(v[i]) - nm);
+                        run_sum = (run_max > -INFINITY ? run_sum * expf(run_max - nm) : 0.f) + e;
+                        run_max = nm;
+                    }
                 } else if (PASS == 2) {
                     // brute-force L2: d^2 = |a|^2 + |b|^2 - 2 a.b ; keep the two nearest (lowest index on ties)
 #pragma unroll
@@ -244,10 +252,31 @@ __global__ void __launch_bounds__(256, 1) match_rows_tc(const __grid_constant__ 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&t_empty[s]);
         }
-        if (row < nr) {
-            if (PASS == 0) row_lse[(size_t)rs_r * k_cap + row] = run_max + logf(run_sum);
-            else { best_val[(size_t)rs_r * k_cap + row] = bv; best_idx[(size_t)rs_r * k_cap + row] = bi; }
-            if (PASS == 2) row_lse[(size_t)rs_r * k_cap + row] = b2v;
+        // merge the two column halves of every row: group 1 publishes, group 0 combines and stores
+        if (grp == 1) {
+            s_mrg[row_local] = PASS == 0 ? run_max : bv;
+            s_mrg[128 + row_local] = PASS == 0 ? run_sum : b2v;
+            s_mrg[256 + row_local] = __int_as_float(bi);
+        }
+        tc::named_bar_sync(2, 128 * MT_EPI_GROUPS);
+        if (grp == 0 && row < nr) {
+            const float o0 = s_mrg[row_local], o1 = s_mrg[128 + row_local];
+            const int oi = __float_as_int(s_mrg[256 + row_local]);
+            if (PASS == 0) {
+                const float nm = fmaxf(run_max, o0);
+                const float tot = (run_max > -INFINITY ? run_sum * expf(run_max - nm) : 0.f) + (o0 > -INFINITY ? o1 * expf(o0 - nm) : 0.f);
+                row_lse[(size_t)rs_r * k_cap + row] = nm + logf(tot);
+            } else if (PASS == 1) {
+                if (oi >= 0 && (bi < 0 || o0 > bv || (o0 == bv && oi < bi))) { bv = o0; bi = oi; }
+                best_val[(size_t)rs_r * k_cap + row] = bv; best_idx[(size_t)rs_r * k_cap + row] = bi;
+            } else {
+                // two smallest of {bv, b2v, o0, o1}; nearest keeps the lowest column index on ties
+                float n1 = bv, n2 = b2v; int ni = bi;
+                if (o0 < n1 || (o0 == n1 && oi >= 0 && oi < ni)) { n2 = fminf(n1, o1); n1 = o0; ni = oi; }
+                else n2 = fminf(n2, o0);
+                best_val[(size_t)rs_r * k_cap + row] = n1; best_idx[(size_t)rs_r * k_cap + row] = ni;
+                row_lse[(size_t)rs_r * k_cap + row] = n2;
+            }
         }
     }
     tc::tc_fence_before();
@@ -278,13 +307,13 @@ int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int 
     CUtensorMap* g_tmap_host = &tc_state(ctx)->match_map;
     dim3 grid(ceil_div(k, MT_BM), pairs, pass == 2 ? 1 : 2);
     if (pass == 2)
-        GNB_KERNEL(ctx, "match_rows_tc<2>", match_rows_tc<2><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
+        GNB_KERNEL(ctx, "match_rows_tc<2>", match_rows_tc<2><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
             *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
     else if (pass == 0)
-        GNB_KERNEL(ctx, "match_rows_tc<0>", match_rows_tc<0><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
+        GNB_KERNEL(ctx, "match_rows_tc<0>", match_rows_tc<0><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
             *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
     else
-        GNB_KERNEL(ctx, "match_rows_tc<1>", match_rows_tc<1><<<grid, 256, MT_SMEM_BYTES, ctx->stream>>>(
+        GNB_KERNEL(ctx, "match_rows_tc<1>", match_rows_tc<1><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
             *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
     return GNB_OK;
 }

@@ -425,6 +425,33 @@ def test_candidate_search_with_tile_cache():
     ctx.close()
 
 
+def test_device_resident_batch_and_config5_parameters():
+    """estimate_batch_device (inputs already in HBM, the bench's `value` path) == estimate_batch (host
+    buffers), at BASELINE config 5's parameters: keypoint cap 2048, 2000 RANSAC hypotheses."""
+    import torch
+
+    blob = _trained_blob()
+    ground = synth.ground_texture(4096, seed=25, n_shapes=200)
+    pairs = [synth.make_pair(ground, s) for s in (0, 1)]
+    cfg = Config(max_batch=2, max_keypoints=2048, ransac_iters=2000)
+    ctx = Context(cfg, weights=blob)
+    pe = PoseEstimator(ctx)
+    host = (np.stack([p.frame for p in pairs]), np.stack([p.tile for p in pairs]), np.stack([p.dem for p in pairs]),
+            np.stack([p.k for p in pairs]), np.stack([p.affine for p in pairs]))
+    a = pe.estimate_batch(*host)
+    dev = tuple(torch.from_numpy(x).cuda() for x in host)
+    b = pe.estimate_batch_device(*dev)
+    for ra, rb, p in zip(a, b, pairs):
+        assert ra.ok and rb.ok
+        assert ra.n_kp_qry == 2048 and ra.n_kp_ref == 2048
+        assert (ra.n_matches, ra.n_inliers, ra.best_hypothesis) == (rb.n_matches, rb.n_inliers, rb.best_hypothesis)
+        np.testing.assert_array_equal(ra.r, rb.r)
+        np.testing.assert_array_equal(ra.ecef, rb.ecef)
+        assert np.abs(ra.camera_center - (-p.r_gt.T @ p.t_gt).ravel()).max() < 3.0
+        assert abs(np.linalg.norm(ra.quat) - 1.0) < 1e-12
+    ctx.close()
+
+
 def test_full_size_properties():
     """BASELINE config 2 shape (1280x720 frame, 1024x1024 raster): size-independent properties."""
     blob = _trained_blob()
