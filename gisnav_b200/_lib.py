@@ -82,6 +82,7 @@ SIGNATURES = {
     "gnb_pose_batch": (_I, [_VP, _I, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, C.POINTER(GnbPoseResult)]),
     "gnb_pose_candidates": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, C.POINTER(GnbPoseResult), C.POINTER(_I)]),
     "gnb_cache_clear": (_I, [_VP]),
+    "gnb_rotate_crop": (_I, [_VP, _VP, _I, _VP, _I, _I, C.c_double, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "gnb_dense": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "gnb_layer_activation": (_I, [_VP, C.c_char_p, _VP, C.c_size_t]),
     "gnb_select_keypoints": (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, C.POINTER(_I)]),

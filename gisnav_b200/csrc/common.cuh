@@ -105,6 +105,8 @@ struct gnb_ctx {
     int* c_kp_count;                // [cache_cap]
     bf16* c_mproj;                  // [cache_cap][K][256]
     float* c_mlogit;                // [cache_cap][K]
+    uint8_t* warp_buf;              // staging of gnb_rotate_crop's host-buffer path (warp.cu), grow-only
+    size_t warp_bytes;
     void* tc_state;                 // TcState* (tc_common.cuh): tensor maps bound to this context's buffers
     // profiling
     int prof_on;

@@ -156,6 +156,21 @@ int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int 
                         gnb_pose_result* results, int* n_cache_hits);
 int gnb_cache_clear(gnb_ctx* ctx);
 
+/* ---- the step in front of the path: StereoNode's rotate + centre-crop ------ */
+
+/* StereoNode._rotate_and_crop_center (ros/gisnav/gisnav/core/stereo_node.py:292-335) with the
+ * grayscale conversion in front of it (cv2.cvtColor BGR2GRAY, stereo_node.py:239) fused in:
+ * ortho u8 [h,w,channels] (channels 1 = gray, 3 = BGR interleaved), dem u8 [h,w] or NULL ->
+ * out_ref u8 [crop_h,crop_w], out_dem u8 [crop_h,crop_w] = cv2.warpAffine(stack,
+ * getRotationMatrix2D((w//2,h//2), angle, 1), (w,h))[dy:dy+crop_h, dx:dx+crop_w], bit-identical to
+ * OpenCV's fixed-point INTER_LINEAR / BORDER_CONSTANT path.  out_rotation6 (optional) = the 2x3
+ * rotation matrix; out_inverse9 (optional) = the 3x3 matrix mapping cropped-frame pixels back to
+ * the original raster (second return value of the reference function).  Buffers all host or all
+ * device (on_device). */
+int gnb_rotate_crop(gnb_ctx* ctx, const uint8_t* ortho, int channels, const uint8_t* dem, int h, int w,
+                    double angle_degrees, int crop_h, int crop_w, int on_device, uint8_t* out_ref, uint8_t* out_dem,
+                    double* out_rotation6, double* out_inverse9);
+
 /* ---- stage-isolated hooks (parity tests feed the oracle's intermediate into one stage) ------ */
 
 /* K1: image -> score map f32 [h,w] and L2-normalised dense descriptors f32 [h/8,w/8,256]. */

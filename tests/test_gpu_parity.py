@@ -478,3 +478,80 @@ def test_full_size_properties():
     assert res is not None
     assert np.abs(res.camera_center - (-pair.r_gt.T @ pair.t_gt).ravel()).max() < 3.0
     ctx.close()
+
+
+# ---- StereoNode rotate + centre-crop: bit-exact vs the reference's cv2 calls --------
+def test_stereo_rotate_crop_bit_exact_vs_cv2(rand_blob):
+    from gisnav_b200.stereo import StereoAligner
+    from oracle import stereo_ref
+
+    ctx = _ctx(rand_blob)
+    sa = StereoAligner(ctx)
+    # committed outputs of the reference call sequence (tools/make_golden.py, stereo_node.py:239,306-335)
+    g = dict(np.load(os.path.join(GOLDEN, "stereo_cv2.npz")))
+    stack = np.dstack((g["gray"], g["dem"]))
+    for ang in (0, 45, 90, 135, 180, 225, 270, 315):
+        ref, dem, inv = sa.align(g["ortho_bgr"], g["dem"], ang, (72, 104))      # BGR in: gray conversion fused
+        np.testing.assert_array_equal(ref, g[f"crop_{ang}"][:, :, 0])
+        np.testing.assert_array_equal(dem, g[f"crop_{ang}"][:, :, 1])
+        np.testing.assert_array_equal(inv, g[f"inv_{ang}"])
+        got, inv2 = sa.rotate_and_crop_center(stack, ang, (72, 104))            # the reference's signature
+        np.testing.assert_array_equal(got, g[f"crop_{ang}"])
+        np.testing.assert_array_equal(inv2, g[f"inv_{ang}"])
+    # live against the installed OpenCV: ragged sizes (crop width not a multiple of 4), arbitrary angles, no DEM
+    rng = np.random.default_rng(3)
+    for (h, w), shape in (((301, 413), (121, 163)), ((97, 97), (33, 50)), ((64, 64), (64, 64))):
+        img = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+        for ang in (45, 17.3, -101.5, 359.0):
+            want, inv_want = stereo_ref.cv2_rotate_and_crop_center(img, ang, shape)
+            got, inv = sa.rotate_and_crop_center(img, ang, shape)
+            np.testing.assert_array_equal(got, want)
+            np.testing.assert_array_equal(inv, inv_want)
+            one, _ = sa.rotate_and_crop_center(np.ascontiguousarray(img[:, :, 0]), ang, shape)
+            np.testing.assert_array_equal(one, want[:, :, 0])
+    with pytest.raises(_lib.GnbError):
+        sa.rotate_and_crop_center(np.zeros((32, 32), np.uint8), 0, (40, 40))   # crop larger than the raster
+    ctx.close()
+
+
+def test_stereo_full_size_device_path_feeds_the_extractor():
+    """Reference geometry at BASELINE config 2: GISNode requests a square of side ceil(hypot(w, h))
+    (gis_node.py:361-384) = 1469 for a 1280x720 camera; StereoNode rotates it to the yaw bucket and crops
+    to the camera resolution (stereo_node.py:244-248).  Device tensors in, device tensors out, and the
+    cropped raster goes straight into the batch path without a host round-trip."""
+    import torch
+
+    from gisnav_b200.stereo import StereoAligner, map_rotation, world_to_reference_affine
+    from oracle import stereo_ref
+
+    side = 1469
+    ground = synth.ground_texture(2048, seed=5, n_shapes=1500)
+    ortho = np.ascontiguousarray(np.stack([ground[200:200 + side, 300:300 + side]] * 3, axis=-1))
+    ortho[:, :, 1] = np.roll(ortho[:, :, 1], 1, axis=0)
+    dem = np.zeros((side, side), np.uint8)
+    ctx = Context(Config(max_batch=1, max_image_h=1024, max_image_w=1280))
+    sa = StereoAligner(ctx)
+    dev = torch.device("cuda", 0)
+    bucket = map_rotation(50.0, 3.0)
+    assert bucket == 45
+    ref_d, dem_d, inv = sa.align_device(torch.from_numpy(ortho).to(dev), torch.from_numpy(dem).to(dev), bucket, (720, 1280))
+    want, inv_want = stereo_ref.cv2_rotate_and_crop_center(stereo_ref.cv2_orthoimage_stack(ortho, dem), bucket, (720, 1280))
+    np.testing.assert_array_equal(ref_d.cpu().numpy(), want[:, :, 0])
+    np.testing.assert_array_equal(dem_d.cpu().numpy(), want[:, :, 1])
+    np.testing.assert_array_equal(inv, inv_want)
+    # idempotence-style property at full size: four quarter turns of a square crop give the raster back
+    sq = torch.from_numpy(np.ascontiguousarray(ground[:1024, :1024])).to(dev)
+    cur = sq
+    for _ in range(4):
+        cur, _, _ = sa.align_device(cur, None, 90, (1024, 1024))
+    # a quarter turn about (w//2, h//2) of an even-sized raster shifts by one pixel per turn: compare the interior
+    np.testing.assert_array_equal(cur.cpu().numpy()[8:-8, 8:-8], sq.cpu().numpy()[8:-8, 8:-8])
+    # the cropped raster feeds the extractor directly (device-resident)
+    pe = PoseEstimator(ctx)
+    frame = torch.from_numpy(np.ascontiguousarray(want[:, :, 0])).to(dev)   # query = the same view: identity pose geometry
+    f = 0.32 * 1280
+    k = torch.tensor([[f, 0, 640.0], [0, f, 360.0], [0, 0, 1]], dtype=torch.float64, device=dev).reshape(1, 9)
+    aff = torch.tensor(world_to_reference_affine(inv, synth.tile_affine(0.0, 0.0)), dtype=torch.float64, device=dev).reshape(1, 12)
+    res = pe.estimate_batch_device(frame[None].contiguous(), ref_d[None].contiguous(), dem_d[None].contiguous(), k, aff)
+    assert res[0].n_kp_ref > 100 and res[0].n_matches > 50
+    ctx.close()

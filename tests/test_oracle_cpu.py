@@ -251,3 +251,50 @@ def test_bf_ratio_oracle_on_sift():
     np.testing.assert_array_equal(idx[:, 0], np.nonzero(keep)[0])
     np.testing.assert_array_equal(idx[:, 1], order[keep, 0])
     np.testing.assert_array_equal(dist, d1[keep])
+
+
+# ---- StereoNode rotate + centre-crop ---------------------------------------
+def test_stereo_oracle_bit_exact_vs_cv2():
+    """The numpy restatement of cvtColor / getRotationMatrix2D / warpAffine against the installed OpenCV
+    executing the reference's own call sequence (stereo_node.py:239,306-335)."""
+    import cv2
+
+    from oracle import stereo_ref
+
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, (131, 77, 3), dtype=np.uint8)
+    np.testing.assert_array_equal(stereo_ref.bgr_to_gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    for (h, w), shape in (((735, 735), (360, 640)), ((300, 412), (120, 160)), ((97, 97), (33, 50))):
+        stack = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+        for ang in (0, 45, 90, 135, 180, 225, 270, 315, 17.3, -101.5):
+            np.testing.assert_array_equal(stereo_ref.rotation_matrix_2d((w // 2, h // 2), ang),
+                                          cv2.getRotationMatrix2D((w // 2, h // 2), ang, 1.0))
+            want, inv_want = stereo_ref.cv2_rotate_and_crop_center(stack, ang, shape)
+            got, inv_got = stereo_ref.rotate_and_crop_center(stack, ang, shape)
+            np.testing.assert_array_equal(got, want)
+            np.testing.assert_array_equal(inv_got, inv_want)
+
+
+def test_stereo_oracle_golden_and_bookkeeping():
+    from conftest import GOLDEN
+    from oracle import stereo_ref, tail_ref
+
+    g = dict(np.load(os.path.join(GOLDEN, "stereo_cv2.npz")))
+    np.testing.assert_array_equal(stereo_ref.bgr_to_gray(g["ortho_bgr"]), g["gray"])
+    stack = np.dstack((g["gray"], g["dem"]))
+    for ang in (0, 45, 90, 135, 180, 225, 270, 315):
+        got, inv = stereo_ref.rotate_and_crop_center(stack, ang, (72, 104))
+        np.testing.assert_array_equal(got, g[f"crop_{ang}"])
+        np.testing.assert_array_equal(inv, g[f"inv_{ang}"])
+    # yaw buckets (stereo_node.py:208-216)
+    assert [stereo_ref.map_rotation(y, 0) for y in (0, 22, 23, 67, 68, 337, 338, 359.9, -10)] == [0, 0, 45, 45, 90, 315, 0, 0, 0]
+    # CRS composition: a cropped-frame pixel must land on the lon/lat of the original-raster pixel it came from
+    # (with the x/y swap the reference applies, stereo_node.py:160-162)
+    a = synth.tile_affine(1000.0, 2000.0)
+    inv = g["inv_45"]
+    comp = stereo_ref.world_to_reference_affine(inv, a)
+    p = np.array([10.0, 20.0, 0.0, 1.0])
+    src = inv @ np.array([10.0, 20.0, 1.0])
+    np.testing.assert_allclose(comp @ p, a @ np.array([src[1], src[0], 0.0, 1.0]), rtol=0, atol=1e-9)
+    s = tail_ref.affine_to_proj(comp)
+    np.testing.assert_array_equal(tail_ref.proj_to_affine(s), comp)

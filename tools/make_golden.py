@@ -11,6 +11,9 @@
   pin the oracle against drift; the oracle itself is cross-checked against the independent
   ``transformers`` restatements in tests/test_oracle_cpu.py.
 
+* ``stereo_cv2.npz`` — inputs and outputs of the reference's rotate + centre-crop call sequence
+  (stereo_node.py:239,306-335) executed here; pins oracle/stereo_ref.py and csrc/warp.cu.
+
     python tools/make_golden.py
 """
 import os
@@ -66,9 +69,28 @@ def stage_fixtures():
     np.savez_compressed(os.path.join(OUT, "stages_small.npz"), **res)
 
 
+def stereo_fixtures():
+    """Outputs of the REFERENCE's own rotate+crop call sequence (cv2.cvtColor + cv2.getRotationMatrix2D +
+    cv2.warpAffine + slice, stereo_node.py:239,306-335) on a small seeded orthoimage/DEM, executed here."""
+    from oracle import stereo_ref
+
+    rng = np.random.default_rng(7)
+    g = synth.ground_texture(256, seed=9, n_shapes=120)
+    ortho = np.stack([np.roll(g, 3 * c, axis=c % 2)[:149, :149] for c in range(3)], axis=-1).astype(np.uint8)  # BGR
+    dem = rng.integers(0, 40, (149, 149), dtype=np.uint8)
+    stack = stereo_ref.cv2_orthoimage_stack(ortho, dem)
+    res = {"ortho_bgr": ortho, "dem": dem, "gray": stack[:, :, 0], "cv2_version": np.array(cv2.__version__)}
+    for ang in (0, 45, 90, 135, 180, 225, 270, 315):
+        cropped, inv = stereo_ref.cv2_rotate_and_crop_center(stack, ang, (72, 104))
+        res[f"crop_{ang}"], res[f"inv_{ang}"] = np.ascontiguousarray(cropped), inv
+    np.savez_compressed(os.path.join(OUT, "stereo_cv2.npz"), **res)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    pnp_fixtures()
-    stage_fixtures()
+    if "--only-stereo" not in sys.argv:
+        pnp_fixtures()
+        stage_fixtures()
+    stereo_fixtures()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
