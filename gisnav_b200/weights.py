@@ -118,3 +118,86 @@ def load(path: str | None = None) -> bytes:
         blob = f.read()
     unpack(blob)  # validates
     return blob
+
+
+# ---- LightGlue transformer layers --------------------------------------------
+# The reference matcher runs nine self+cross attention layers in front of the assignment head
+# (LightGlueMatcher(..., n_layers=9), ros/gisnav/gisnav/core/pose_node.py:109-121).  Their parameters
+# travel in a second, optional blob: 16-byte header b"GNBL", u32 version, u32 n_layers, u32 n_floats,
+# then float32 tensors in the order of `layer_tensors(n_layers)` (Linear weights are [out, in]).
+LAYER_MAGIC = b"GNBL"
+LAYER_VERSION = 1
+LG_HEADS = 4
+LG_HIDDEN = 2 * DESC_DIM
+
+
+def layer_tensors(n_layers: int) -> "OrderedDict[str, Tuple[int, ...]]":
+    t: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    t["lg.pos.weight"] = (DESC_DIM // LG_HEADS // 2, 2)   # rotary angle projector, no bias
+    for i in range(n_layers):
+        for blk in ("self", "cross"):
+            p = f"lg.{i}.{blk}"
+            for proj in ("q", "k", "v", "o"):
+                t[f"{p}.{proj}.weight"] = (DESC_DIM, DESC_DIM)
+                t[f"{p}.{proj}.bias"] = (DESC_DIM,)
+            t[f"{p}.fc1.weight"] = (LG_HIDDEN, LG_HIDDEN)
+            t[f"{p}.fc1.bias"] = (LG_HIDDEN,)
+            t[f"{p}.ln.weight"] = (LG_HIDDEN,)
+            t[f"{p}.ln.bias"] = (LG_HIDDEN,)
+            t[f"{p}.fc2.weight"] = (DESC_DIM, LG_HIDDEN)
+            t[f"{p}.fc2.bias"] = (DESC_DIM,)
+    return t
+
+
+def layer_floats(n_layers: int) -> int:
+    return int(sum(int(np.prod(s)) for s in layer_tensors(n_layers).values()))
+
+
+def pack_layers(params: Dict[str, np.ndarray], n_layers: int) -> bytes:
+    table = layer_tensors(n_layers)
+    chunks = [LAYER_MAGIC + struct.pack("<III", LAYER_VERSION, n_layers, layer_floats(n_layers))]
+    for name, shape in table.items():
+        a = np.ascontiguousarray(np.asarray(params[name], dtype=np.float32))
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+        chunks.append(a.astype("<f4").tobytes())
+    return b"".join(chunks)
+
+
+def unpack_layers(blob: bytes) -> Tuple[Dict[str, np.ndarray], int]:
+    if len(blob) < HEADER_BYTES or blob[:4] != LAYER_MAGIC:
+        raise ValueError("not a GNBL layer blob")
+    version, n_layers, n = struct.unpack("<III", blob[4:16])
+    if version != LAYER_VERSION or n != layer_floats(n_layers) or len(blob) != HEADER_BYTES + 4 * n:
+        raise ValueError("layer blob version/size mismatch")
+    flat = np.frombuffer(blob, dtype="<f4", offset=HEADER_BYTES)
+    out: Dict[str, np.ndarray] = {}
+    off = 0
+    for name, shape in layer_tensors(n_layers).items():
+        cnt = int(np.prod(shape))
+        out[name] = flat[off: off + cnt].reshape(shape).copy()
+        off += cnt
+    return out, n_layers
+
+
+def layers_random_init(n_layers: int, seed: int = 0, residual_zero: bool = False) -> Dict[str, np.ndarray]:
+    """Seeded init of the transformer layers (no LightGlue checkpoint is reachable offline).
+
+    ``residual_zero=True`` zeroes every block's last linear layer (the usual zero-init of a residual
+    branch): each block then adds exactly 0 to the residual stream, so untrained layers run their full
+    arithmetic yet leave the descriptors — and therefore the matches of the trained head — unchanged.
+    """
+    rng = np.random.default_rng(seed)
+    p: Dict[str, np.ndarray] = {}
+    for name, shape in layer_tensors(n_layers).items():
+        if name == "lg.pos.weight":
+            p[name] = (rng.standard_normal(shape) * 4.0).astype(np.float32)
+        elif name.endswith("ln.weight"):
+            p[name] = (1.0 + 0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif name.endswith(".bias"):
+            p[name] = (0.05 * rng.standard_normal(shape)).astype(np.float32)
+        else:
+            p[name] = (rng.standard_normal(shape) / np.sqrt(shape[1])).astype(np.float32)
+        if residual_zero and ".fc2." in name:
+            p[name] = np.zeros(shape, np.float32)
+    return p

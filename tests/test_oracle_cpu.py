@@ -298,3 +298,63 @@ def test_stereo_oracle_golden_and_bookkeeping():
     np.testing.assert_allclose(comp @ p, a @ np.array([src[1], src[0], 0.0, 1.0]), rtol=0, atol=1e-9)
     s = tail_ref.affine_to_proj(comp)
     np.testing.assert_array_equal(tail_ref.proj_to_affine(s), comp)
+
+
+# ---- LightGlue transformer layers vs transformers' restatement ---------------
+def test_lightglue_layers_match_transformers():
+    from transformers import LightGlueConfig
+    from transformers.models.lightglue.modeling_lightglue import (LightGluePositionalEncoder, LightGlueTransformerLayer,
+                                                                  normalize_keypoints)
+
+    from gisnav_b200 import weights as W
+    from oracle import lightglue_ref
+
+    n_layers, n = 3, 37
+    lp = W.layers_random_init(n_layers, seed=4)
+    blob = W.pack_layers(lp, n_layers)
+    lp2, nl = W.unpack_layers(blob)
+    assert nl == n_layers and all(np.array_equal(lp[k], lp2[k]) for k in lp)
+    cfg = LightGlueConfig(num_hidden_layers=n_layers)
+    cfg._attn_implementation = "eager"
+    pos = LightGluePositionalEncoder(cfg).eval()
+    pos.projector.weight.data = torch.from_numpy(lp["lg.pos.weight"])
+    layers = []
+    for i in range(n_layers):
+        layer = LightGlueTransformerLayer(cfg, i).eval()
+        for blk, att, mlp in (("self", layer.self_attention, layer.self_mlp), ("cross", layer.cross_attention, layer.cross_mlp)):
+            for short, mod in (("q", att.q_proj), ("k", att.k_proj), ("v", att.v_proj), ("o", att.o_proj),
+                               ("fc1", mlp.fc1), ("fc2", mlp.fc2), ("ln", mlp.layer_norm)):
+                mod.weight.data = torch.from_numpy(lp[f"lg.{i}.{blk}.{short}.weight"])
+                mod.bias.data = torch.from_numpy(lp[f"lg.{i}.{blk}.{short}.bias"])
+        layers.append(layer)
+    rng = np.random.default_rng(8)
+    d = rng.standard_normal((2, n, 256)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=2, keepdims=True)
+    hw = (240, 320)
+    kp = (rng.random((2, n, 2)) * np.array([hw[1], hw[0]])).astype(np.float32)
+    with torch.no_grad():
+        kpn = normalize_keypoints(torch.from_numpy(kp), hw[0], hw[1])
+        np.testing.assert_allclose(lightglue_ref.normalize_keypoints(kp[0], *hw), kpn[0].numpy(), rtol=1e-6, atol=1e-7)
+        emb = pos(kpn)[0]
+        x = torch.from_numpy(d)
+        for layer in layers:
+            x = layer(x, emb, attention_mask=None)[0]
+    hidden = []
+    y0, y1 = lightglue_ref.forward(d[0], kp[0], hw, d[1], kp[1], hw, lp, n_layers, emulate_bf16=False, hidden=hidden)
+    assert len(hidden) == n_layers
+    scale = float(x.abs().max())
+    np.testing.assert_allclose(y0, x[0].numpy(), rtol=0, atol=2e-5 * scale)
+    np.testing.assert_allclose(y1, x[1].numpy(), rtol=0, atol=2e-5 * scale)
+    # the bf16-operand form the CUDA path implements stays close to the fp32 form
+    z0, z1 = lightglue_ref.forward(d[0], kp[0], hw, d[1], kp[1], hw, lp, n_layers, emulate_bf16=True)
+    assert np.abs(z0 - y0).max() < 0.05 * scale and np.abs(z1 - y1).max() < 0.05 * scale
+    # ragged sets (own semantics: no padding, every key is real) and the empty case
+    r0, r1 = lightglue_ref.forward(d[0], kp[0], hw, d[1][:20], kp[1][:20], hw, lp, n_layers)
+    assert r0.shape == (n, 256) and r1.shape == (20, 256) and np.isfinite(r0).all()
+    e0, e1 = lightglue_ref.forward(d[0][:0], kp[0][:0], hw, d[1], kp[1], hw, lp, n_layers)
+    assert e0.shape == (0, 256) and np.array_equal(e1, d[1])
+    # residual-zero init leaves descriptors untouched (what bench.py --matcher-layers uses with the trained head)
+    lz = W.layers_random_init(2, seed=1, residual_zero=True)
+    u0, u1 = lightglue_ref.forward(d[0], kp[0], hw, d[1], kp[1], hw, lz, 2)
+    np.testing.assert_array_equal(u0, d[0])
+    np.testing.assert_array_equal(u1, d[1])
