@@ -76,6 +76,10 @@ SIGNATURES = {
     "gnb_profile_read": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_extract": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_match": (_I, [_VP, _VP, _I, _VP, _I, _I, _VP, _VP, _I, C.POINTER(_I)]),
+    "gnb_set_matcher_layers": (_I, [_VP, _VP, C.c_size_t]),
+    "gnb_matcher_layers": (_I, [_VP]),
+    "gnb_match_lightglue": (_I, [_VP, _VP, _VP, _I, _F, _F, _VP, _VP, _I, _F, _F, _I, _VP, _VP, _I, C.POINTER(_I)]),
+    "gnb_refined_descriptors": (_I, [_VP, _I, _VP, _I]),
     "gnb_knn_ratio_match": (_I, [_VP, _VP, _I, _VP, _I, _I, _F, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_solve_pnp": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, C.POINTER(_I)]),
     "gnb_geodetic_tail": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),

@@ -80,6 +80,19 @@ class Context:
             raise _lib.GnbError(rc, msg)
         return rc
 
+    def set_matcher_layers(self, blob: Optional[bytes]) -> None:
+        """Load (or with ``None`` unload) the LightGlue transformer layers that run in front of the assignment
+        head (``gisnav_b200.weights.pack_layers``; reference: ``n_layers=9``, pose_node.py:109-121)."""
+        if blob is None:
+            self.check(self._lib.gnb_set_matcher_layers(self._h, None, 0))
+            return
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.gnb_set_matcher_layers(self._h, C.cast(buf, C.c_void_p), len(blob)))
+
+    @property
+    def matcher_layers(self) -> int:
+        return int(self._lib.gnb_matcher_layers(self._h))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.gnb_launch_count(self._h))

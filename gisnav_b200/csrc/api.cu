@@ -187,6 +187,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    gnb_lightglue_free(ctx);
     gnb_conv_free(ctx);
     gnb_match_free(ctx);
     ConvWorkspace& cw = ctx->cw;
@@ -341,8 +342,15 @@ __global__ void widen_idx_kernel(const int* __restrict__ in, long long* __restri
     if (i < n2) out[i] = (long long)in[i];
 }
 
-static int load_descs(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device) {
+struct KpArgs { const float *kp_a, *kp_b; float ha, wa, hb, wb; };
+
+static int load_descs(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device,
+                      const KpArgs* kps = nullptr) {
     const int k = ctx->cfg.max_keypoints, sb = ctx->cfg.max_batch;
+    if (ctx->lg_state && !kps) {
+        GNB_SET_ERR(ctx, "the matcher has transformer layers: keypoints are required (gnb_match_lightglue)");
+        return GNB_E_INVALID;
+    }
     if (n_a < 0 || n_b < 0 || n_a > k || n_b > k) {
         GNB_SET_ERR(ctx, "descriptor count exceeds max_keypoints=%d", k);
         return GNB_E_CAPACITY;
@@ -351,22 +359,53 @@ static int load_descs(gnb_ctx* ctx, const float* desc_a, int n_a, const float* d
     if (n_b) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->desc_f32 + (size_t)sb * k * 256, desc_b, sizeof(float) * 256 * n_b, kind_in(on_device), ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n_a, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count + sb, &n_b, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (kps && n_a && n_b) {
+        GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_xy, kps->kp_a, sizeof(float) * 2 * n_a, kind_in(on_device), ctx->stream));
+        GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_xy + (size_t)sb * k * 2, kps->kp_b, sizeof(float) * 2 * n_b, kind_in(on_device), ctx->stream));
+    }
     GNB_SYNC(ctx);  // n_a/n_b live on the caller's stack
     int rc;
+    if (kps && (rc = gnb_lightglue_forward(ctx, 1, 0, sb, kps->ha, kps->wa, kps->hb, kps->wb))) return rc;
     if ((rc = gnb_match_project(ctx, 0, 1))) return rc;
     if ((rc = gnb_match_project(ctx, sb, 1))) return rc;
     return GNB_OK;
 }
 
+static int match_impl(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device, const KpArgs* kps,
+                      int64_t* out_idx, float* out_score, int cap, int* n_out);
+
 extern "C" int gnb_match(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device,
                          int64_t* out_idx, float* out_score, int cap, int* n_out) {
+    return match_impl(ctx, desc_a, n_a, desc_b, n_b, on_device, nullptr, out_idx, out_score, cap, n_out);
+}
+
+extern "C" int gnb_match_lightglue(gnb_ctx* ctx, const float* desc_a, const float* kp_a, int n_a, float h_a, float w_a,
+                                   const float* desc_b, const float* kp_b, int n_b, float h_b, float w_b, int on_device,
+                                   int64_t* out_idx, float* out_score, int cap, int* n_out) {
+    if ((n_a > 0 && !kp_a) || (n_b > 0 && !kp_b)) return GNB_E_INVALID;
+    KpArgs kps{kp_a, kp_b, h_a, w_a, h_b, w_b};
+    return match_impl(ctx, desc_a, n_a, desc_b, n_b, on_device, &kps, out_idx, out_score, cap, n_out);
+}
+
+// descriptors of the last gnb_match / gnb_match_lightglue call after the transformer layers (parity hook)
+extern "C" int gnb_refined_descriptors(gnb_ctx* ctx, int side, float* out, int n) {
+    if (!ctx || !out || n < 0 || n > ctx->cfg.max_keypoints || side < 0 || side > 1) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t off = side ? (size_t)ctx->cfg.max_batch * ctx->cfg.max_keypoints * 256 : 0;
+    if (n) GNB_CUDA(ctx, cudaMemcpyAsync(out, ctx->desc_f32 + off, sizeof(float) * 256 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_SYNC(ctx);
+    return GNB_OK;
+}
+
+static int match_impl(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device, const KpArgs* kps,
+                      int64_t* out_idx, float* out_score, int cap, int* n_out) {
     if (!ctx || !n_out) return GNB_E_INVALID;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     *n_out = 0;
     if (n_a == 0 || n_b == 0) return GNB_OK;
     if (!desc_a || !desc_b) return GNB_E_INVALID;
     int rc;
-    if ((rc = load_descs(ctx, desc_a, n_a, desc_b, n_b, on_device))) return rc;
+    if ((rc = load_descs(ctx, desc_a, n_a, desc_b, n_b, on_device, kps))) return rc;
     if ((rc = gnb_match_pairs(ctx, 1, 0, ctx->cfg.max_batch))) return rc;
     int n = 0;
     if ((rc = read_count(ctx, ctx->match_count, &n))) return rc;
@@ -505,6 +544,8 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
     if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, ht, wt, sb))) return rc;
     if ((rc = gnb_describe(ctx, batch, ht, wt, sb))) return rc;
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_params, 0));
+    // transformer layers of the reference matcher (pose_node.py:109-121), when a layer blob is loaded
+    if ((rc = gnb_lightglue_forward(ctx, batch, 0, sb, (float)hq, (float)wq, (float)ht, (float)wt))) return rc;
     if ((rc = gnb_match_project(ctx, 0, batch))) return rc;
     if ((rc = gnb_match_project(ctx, sb, batch))) return rc;
     if ((rc = gnb_match_pairs(ctx, batch, 0, sb))) return rc;
@@ -547,6 +588,12 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
     if (!ctx || !frame || !tiles || !k9 || !affine12 || !results || n_tiles < 1) return GNB_E_INVALID;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_tiles > ctx->cfg.max_batch) { GNB_SET_ERR(ctx, "n_tiles %d exceeds max_batch %d", n_tiles, ctx->cfg.max_batch); return GNB_E_CAPACITY; }
+    if (ctx->lg_state) {
+        // with transformer layers the raster features depend on the query they are paired with, so the per-raster
+        // cache of projected descriptors does not apply
+        GNB_SET_ERR(ctx, "candidate search with the raster feature cache runs the head-only matcher; unload the layers first");
+        return GNB_E_INVALID;
+    }
     int rc;
     if ((rc = check_image(ctx, hq, wq)) || (rc = check_image(ctx, ht, wt))) return rc;
     const int sb = ctx->cfg.max_batch;

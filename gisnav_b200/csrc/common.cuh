@@ -107,6 +107,7 @@ struct gnb_ctx {
     float* c_mlogit;                // [cache_cap][K]
     uint8_t* warp_buf;              // staging of gnb_rotate_crop's host-buffer path (warp.cu), grow-only
     size_t warp_bytes;
+    void* lg_state;                 // LgState* (lightglue.cu): transformer layers in front of the head, NULL = head only
     void* tc_state;                 // TcState* (tc_common.cuh): tensor maps bound to this context's buffers
     // profiling
     int prof_on;
@@ -189,3 +190,8 @@ int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, in
 int gnb_tail_device(gnb_ctx* ctx, const double* r9, const double* t3, const double* affine12, int ref_h, int ref_w,
                     double* ecef3, double* quat4, double* lla3);
 int gnb_ensure_stage(gnb_ctx* ctx, size_t floats_a, size_t floats_b);
+
+// lightglue.cu
+void gnb_lightglue_free(gnb_ctx* ctx);
+// run the transformer layers in place on desc_f32 for pairs (slot_a0 + p, slot_b0 + p); no-op without layers
+int gnb_lightglue_forward(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, float ha, float wa, float hb, float wb);

@@ -8,8 +8,12 @@ with ``self._matcher = LightGlueMatcher("sift", {... "filter_threshold": 0.5 ...
 (pose_node.py:109-121).  Returns ``(dists [K,1] float32, idxs [K,2] int64)``; column 0 indexes the
 first descriptor set, column 1 the second (pose_node.py:296-297).  torch tensors are the
 interchange type only; CUDA tensors are consumed and produced in place (no host round trip).
-The LAF arguments are accepted and ignored: the assignment head does not use keypoint geometry
-(the positional encoder lives in the transformer layers).
+With no layer blob loaded the matcher is the LightGlue assignment head and the LAF arguments are
+ignored.  After ``ctx.set_matcher_layers(blob)`` the transformer layers of the reference matcher run
+in front of the head; the keypoint centres are then read from the LAFs
+(``get_laf_center``: ``lafs[0, :, :, 2]``, pose_node.py:267-276) and normalised by ``hw1`` / ``hw2`` or,
+when the caller passes none — the reference does not (pose_node.py:285-287) — by the largest keypoint
+coordinate per axis, as kornia's LightGlueMatcher does.
 """
 from __future__ import annotations
 
@@ -33,7 +37,18 @@ class KeypointMatcher:
     def eval(self):
         return self
 
-    def match_arrays(self, desc1: np.ndarray, desc2: np.ndarray):
+    @staticmethod
+    def _hw(kp: np.ndarray, hw):
+        if hw is not None:
+            return float(hw[0]), float(hw[1])
+        if kp.shape[0] == 0:
+            return 1.0, 1.0
+        m = kp.max(axis=0)
+        return float(m[1]), float(m[0])
+
+    def match_arrays(self, desc1: np.ndarray, desc2: np.ndarray, kp1: Optional[np.ndarray] = None,
+                     kp2: Optional[np.ndarray] = None, hw1=None, hw2=None):
+        """desc f32 [N,256] / [M,256] (+ pixel keypoints f32 [N,2] / [M,2] when layers are loaded)."""
         d1 = np.ascontiguousarray(desc1, np.float32)
         d2 = np.ascontiguousarray(desc2, np.float32)
         if d1.ndim != 2 or d2.ndim != 2 or (d1.size and d1.shape[1] != _lib.DESC_DIM) or (d2.size and d2.shape[1] != _lib.DESC_DIM):
@@ -42,16 +57,45 @@ class KeypointMatcher:
         idx = np.empty((cap, 2), np.int64)
         sc = np.empty((cap,), np.float32)
         n = C.c_int(0)
-        self.ctx.check(self.ctx._lib.gnb_match(self.ctx.handle, ptr(d1), d1.shape[0], ptr(d2), d2.shape[0], 0, ptr(idx),
-                                               ptr(sc), cap, C.byref(n)))
+        if kp1 is None or kp2 is None:
+            if self.ctx.matcher_layers:
+                raise ValueError("transformer layers are loaded: the matcher needs keypoints (pass lafs or kp1/kp2)")
+            self.ctx.check(self.ctx._lib.gnb_match(self.ctx.handle, ptr(d1), d1.shape[0], ptr(d2), d2.shape[0], 0, ptr(idx),
+                                                   ptr(sc), cap, C.byref(n)))
+        else:
+            k1 = np.ascontiguousarray(kp1, np.float32).reshape(-1, 2)
+            k2 = np.ascontiguousarray(kp2, np.float32).reshape(-1, 2)
+            if k1.shape[0] != d1.shape[0] or k2.shape[0] != d2.shape[0]:
+                raise ValueError("one keypoint per descriptor expected")
+            (h1, w1), (h2, w2) = self._hw(k1, hw1), self._hw(k2, hw2)
+            self.ctx.check(self.ctx._lib.gnb_match_lightglue(
+                self.ctx.handle, ptr(d1), ptr(k1), d1.shape[0], h1, w1, ptr(d2), ptr(k2), d2.shape[0], h2, w2, 0,
+                ptr(idx), ptr(sc), cap, C.byref(n)))
         return sc[: n.value].reshape(-1, 1).copy(), idx[: n.value].copy()
+
+    def refined_descriptors(self, side: int, n: int) -> np.ndarray:
+        """Descriptors of side 0 / 1 after the transformer layers of the last call (parity hook)."""
+        out = np.empty((n, _lib.DESC_DIM), np.float32)
+        self.ctx.check(self.ctx._lib.gnb_refined_descriptors(self.ctx.handle, side, ptr(out), n))
+        return out
 
     def __call__(self, desc1, desc2, lafs1=None, lafs2=None, hw1=None, hw2=None):
         import torch
 
+        def centers(lafs):
+            # kornia.feature.get_laf_center: lafs [1,N,2,3] -> [N,2]
+            if lafs is None:
+                return None
+            a = lafs.detach().cpu().numpy() if isinstance(lafs, torch.Tensor) else np.asarray(lafs)
+            return np.ascontiguousarray(a.reshape(-1, 2, 3)[:, :, 2], np.float32)
+
         if not isinstance(desc1, torch.Tensor):
-            dists, idx = self.match_arrays(np.asarray(desc1), np.asarray(desc2))
+            dists, idx = self.match_arrays(np.asarray(desc1), np.asarray(desc2), centers(lafs1), centers(lafs2), hw1, hw2)
             return torch.from_numpy(dists), torch.from_numpy(idx)
+        if self.ctx.matcher_layers:
+            dists, idx = self.match_arrays(desc1.detach().cpu().numpy(), desc2.detach().cpu().numpy(), centers(lafs1),
+                                           centers(lafs2), hw1, hw2)
+            return torch.from_numpy(dists).to(desc1.device), torch.from_numpy(idx).to(desc1.device)
         if desc1.is_cuda:
             d1 = desc1.detach().to(torch.float32).contiguous()
             d2 = desc2.detach().to(torch.float32).contiguous()

@@ -106,6 +106,22 @@ int gnb_extract(gnb_ctx* ctx, const uint8_t* image, int h, int w, int stride, in
 int gnb_match(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, int on_device,
               int64_t* out_idx, float* out_score, int cap, int* n_out);
 
+/* The reference matcher's transformer layers — LightGlueMatcher("sift", {"n_layers": 9, "depth_confidence": -1,
+ * "width_confidence": -1, ...}), pose_node.py:109-121 — are optional here: load a GNBL layer blob
+ * (gisnav_b200/weights.py: pack_layers) and every matcher call runs n_layers of self + cross attention in front
+ * of the assignment head (no early exit, no pruning, like the reference's active branch).  blob NULL / nbytes 0
+ * unloads them.  Needs max_keypoints % 8 == 0 and match_impl = 0. */
+int gnb_set_matcher_layers(gnb_ctx* ctx, const void* blob, size_t nbytes);
+int gnb_matcher_layers(const gnb_ctx* ctx); /* number of loaded layers, 0 = head only */
+
+/* matcher(desc1, desc2, lafs1, lafs2) with the keypoint centres of the LAFs (pose_node.py:267-276,285-287):
+ * kp f32 [n,2] pixel (x, y); (h, w) = image size used to normalise them (the reference passes none and kornia
+ * then uses the largest keypoint coordinate per axis — the Python wrapper reproduces that).  Same outputs as
+ * gnb_match.  Works without loaded layers too (keypoints are then unused). */
+int gnb_match_lightglue(gnb_ctx* ctx, const float* desc_a, const float* kp_a, int n_a, float h_a, float w_a,
+                        const float* desc_b, const float* kp_b, int n_b, float h_b, float w_b, int on_device,
+                        int64_t* out_idx, float* out_score, int cap, int* n_out);
+
 /* TwistNode's visual-odometry matcher — self._bf.knnMatch(desc_qry, desc_ref, k=2) + ratio test
  * `m.distance < 0.7 * n.distance` (ros/gisnav/gisnav/core/twist_node.py:95,248,263-267).  desc f32
  * [n,dim], dim <= 256 (SIFT: 128).  out_idx int64 [cap,2] (queryIdx, trainIdx) in query order,
@@ -188,6 +204,8 @@ int gnb_sample_descriptors(gnb_ctx* ctx, const float* dense, int hc, int wc, con
 /* K4 internals: full assignment log-score matrix f32 [n_a,n_b] (small sizes only). */
 int gnb_match_scores(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b,
                      float* out_scores);
+/* transformer internals: descriptors f32 [n,256] of side 0 / 1 after the layers of the last matcher call. */
+int gnb_refined_descriptors(gnb_ctx* ctx, int side, float* out, int n);
 /* K5 internals: per-hypothesis inlier counts int32 [ransac_iters] (-1 = invalid hypothesis) and
  * hypotheses f32 [ransac_iters,12] (R row-major, t) for the last gnb_solve_pnp call. */
 int gnb_ransac_debug(gnb_ctx* ctx, int32_t* out_counts, float* out_hyp, int* out_best);

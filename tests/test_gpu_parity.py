@@ -555,3 +555,86 @@ def test_stereo_full_size_device_path_feeds_the_extractor():
     res = pe.estimate_batch_device(frame[None].contiguous(), ref_d[None].contiguous(), dem_d[None].contiguous(), k, aff)
     assert res[0].n_kp_ref > 100 and res[0].n_matches > 50
     ctx.close()
+
+
+# ---- LightGlue transformer layers in front of the head ------------------------------
+def _lg_inputs(n, m, hw, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((n, 256)).astype(np.float32)
+    shared = min(n, m) * 2 // 3
+    b = np.concatenate([a[:shared] + 0.1 * rng.standard_normal((shared, 256)).astype(np.float32),
+                        rng.standard_normal((m - shared, 256)).astype(np.float32)])
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    kpa = (rng.random((n, 2)) * np.array([hw[1], hw[0]])).astype(np.float32)
+    kpb = (rng.random((m, 2)) * np.array([hw[1], hw[0]])).astype(np.float32)
+    return a, kpa, b, kpb
+
+
+@pytest.mark.parametrize("n_layers,shape", [(1, (128, 128)), (1, (200, 77)), (3, (300, 260)), (2, (5, 130))])
+def test_lightglue_layers_match_oracle(rand_blob, n_layers, shape):
+    """Refined descriptors after the transformer layers vs the CPU oracle with bf16 rounding at the same points:
+    the residual stream differs by fp32 summation order plus the occasional neighbouring-bf16 operand."""
+    from oracle import lightglue_ref
+
+    n, m = shape
+    hw = (240, 320)
+    lp = W.layers_random_init(n_layers, seed=4)
+    ctx = _ctx(rand_blob, max_keypoints=512)
+    ctx.set_matcher_layers(W.pack_layers(lp, n_layers))
+    assert ctx.matcher_layers == n_layers
+    km = KeypointMatcher(ctx)
+    a, kpa, b, kpb = _lg_inputs(n, m, hw, seed=n + m)
+    km.match_arrays(a, b, kpa, kpb, hw, hw)
+    ga, gb = km.refined_descriptors(0, n), km.refined_descriptors(1, m)
+    ra, rb = lightglue_ref.forward(a, kpa, hw, b, kpb, hw, lp, n_layers, emulate_bf16=True)
+    for got, want in ((ga, ra), (gb, rb)):
+        scale = np.abs(want).max()
+        assert np.isfinite(got).all()
+        assert np.abs(got - want).max() <= 0.03 * n_layers * scale, np.abs(got - want).max() / scale
+        assert np.mean(np.abs(got - want)) <= 0.002 * n_layers * scale
+    ctx.close()
+
+
+def test_lightglue_matcher_end_to_end(rand_blob, rand_params):
+    """matcher(desc1, desc2, lafs1, lafs2) with layers loaded: matches vs the oracle (layers + head), the
+    residual-zero init reproducing the head-only matches exactly, image-size inference, empty inputs, unload."""
+    import torch
+
+    from oracle import lightglue_ref, matcher_ref
+
+    n, m, hw = 260, 300, (240, 320)
+    a, kpa, b, kpb = _lg_inputs(n, m, hw, seed=1)
+    ctx = _ctx(rand_blob, max_keypoints=512, match_threshold=0.0)
+    km = KeypointMatcher(ctx)
+    base_sc, base_idx = km.match_arrays(a, b)                      # head only
+    lz = W.layers_random_init(2, seed=1, residual_zero=True)
+    ctx.set_matcher_layers(W.pack_layers(lz, 2))
+    sc, idx = km.match_arrays(a, b, kpa, kpb, hw, hw)
+    np.testing.assert_array_equal(idx, base_idx)                     # zero residual branches: descriptors untouched
+    np.testing.assert_array_equal(sc, base_sc)
+    with pytest.raises(ValueError):
+        km.match_arrays(a, b)                                         # layers need keypoints
+    # random layers through the kornia-style call (LAFs carry the keypoints; no hw => inferred from the keypoints)
+    lp = W.layers_random_init(2, seed=9)
+    for k in list(lp):                                                # keep the refinement a perturbation so matches survive
+        if ".fc2." in k:
+            lp[k] *= 0.1
+    ctx.set_matcher_layers(W.pack_layers(lp, 2))
+    lafs = lambda kp: torch.from_numpy(np.concatenate([np.tile(np.eye(2, dtype=np.float32), (len(kp), 1, 1)), kp[:, :, None]], axis=2))[None]
+    d, i = km(torch.from_numpy(a), torch.from_numpy(b), lafs(kpa), lafs(kpb))
+    assert d.shape[1] == 1 and i.dtype == torch.int64
+    hwa, hwb = lightglue_ref.infer_image_size(kpa), lightglue_ref.infer_image_size(kpb)
+    ra, rb = lightglue_ref.forward(a, kpa, hwa, b, kpb, hwb, lp, 2)
+    want_sc, want_idx = matcher_ref.match(ra, rb, rand_params, threshold=0.0)
+    got = {tuple(r) for r in i.numpy().tolist()}
+    want = {tuple(r) for r in want_idx.tolist()}
+    assert len(want) > 50 and len(got & want) >= 0.95 * len(want), (len(got), len(want), len(got & want))
+    # empty side: nothing to refine, nothing matched
+    e_sc, e_idx = km.match_arrays(a[:0], b, kpa[:0], kpb, hw, hw)
+    assert e_idx.shape == (0, 2)
+    ctx.set_matcher_layers(None)
+    assert ctx.matcher_layers == 0
+    sc2, idx2 = km.match_arrays(a, b)
+    np.testing.assert_array_equal(idx2, base_idx)
+    ctx.close()
