@@ -130,6 +130,7 @@ def workload_config(args, batch):
     return {
         "workload": "config 2: 1280x720 frame vs 1024x1024 orthophoto tile, full extract+match+PnP+WGS84 tail",
         "pairs_per_step_per_gpu": batch, "max_keypoints": args.keypoints, "ransac_iters": args.ransac_iters,
+        "matcher_layers": getattr(args, "matcher_layers", 0),
         "l2_policy": "inputs cycle over distinct pre-staged batches; per-step activation traffic (>1 GB) exceeds the 126 MB L2",
     }
 
@@ -230,6 +231,12 @@ def run_b200(args):
                              max_image_h=1024, max_image_w=1280)
     ctx = gisnav_b200.Context(cfg, device=local, weights_device_ptr=wt.data_ptr(), weights_nbytes=W.BLOB_BYTES)
     pe = gisnav_b200.PoseEstimator(ctx)
+    if args.matcher_layers > 0:
+        # the reference matcher's transformer layers (LightGlue n_layers=9, pose_node.py:109-121).  No LightGlue
+        # checkpoint is reachable offline, so the layers are untrained: residual-zero init (every block's last
+        # linear layer is 0) runs the full arithmetic and leaves the trained head's matches unchanged.
+        ctx.set_matcher_layers(W.pack_layers(W.layers_random_init(args.matcher_layers, seed=0, residual_zero=True),
+                                             args.matcher_layers))
 
     n_sets = 3  # distinct batches cycled through (inputs differ every step)
     lo, _ = sharding.shard_range(world * n_sets * args.batch, rank, world)
@@ -380,7 +387,7 @@ def run_b200(args):
             "pose_rmse_px_vs_ground_truth": float(np.sqrt(np.mean(np.square(err_gt)))) if err_gt else None,
             "pose_rmse_px_vs_cpu_oracle": float(np.sqrt(np.mean(np.square(err_or)))) if err_or else None,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
-            "impl_conv": cfg.conv_impl, "impl_match": cfg.match_impl,
+            "impl_conv": cfg.conv_impl, "impl_match": cfg.match_impl, "matcher_layers": args.matcher_layers,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -398,6 +405,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="pairs per step per GPU")
     ap.add_argument("--keypoints", type=int, default=1024)
     ap.add_argument("--ransac-iters", type=int, default=2048)
+    ap.add_argument("--matcher-layers", type=int, default=0,
+                    help="LightGlue transformer layers in front of the assignment head (0 = head only, the north_star "
+                         "matcher; 9 = the reference's LightGlueMatcher depth, untrained residual-zero weights)")
     ap.add_argument("--cpu-pairs", type=int, default=4, help="pairs timed on the host cores for cpu_baseline (N=1 only)")
     ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step for --impl reference")
     ap.add_argument("--ref-ransac-iters", type=int, default=10,

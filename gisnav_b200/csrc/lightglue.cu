@@ -17,10 +17,10 @@
 //                             FC1  bias, LayerNorm(512) and exact GELU straight from TMEM (BN = 512 =
 //                                  the whole TMEM width, so the full row is resident)
 //                             FC2  bias + residual add into the fp32 stream, bf16 copy for the next GEMM
-//   lg_attn_kernel          two-pass softmax attention per (128 queries, head): pass 0 row max / sum from
-//                           S = q k^T in TMEM; pass 1 recomputes S, writes P = exp(S - lse) as the bf16
-//                           A operand (128B-swizzled smem) of the second MMA O += P V^T-major.  S and P
-//                           never touch HBM.
+//   lg_attn_kernel          two-pass softmax attention per (128 queries, head): pass 0 takes the row max of
+//                           S = q k^T from TMEM; pass 1 recomputes S, writes P = exp(S - max) as the bf16 A
+//                           operand (128B-swizzled smem) of the second MMA O += P V and keeps the fp32 row
+//                           sum that normalises O at the end.  S and P never touch HBM.
 // The fp32 residual stream is ctx->desc_f32 itself (in place), so the head (project_tc) runs unchanged.
 #include "tc_common.cuh"
 
@@ -100,11 +100,14 @@ template <int BN> struct LglCfg {
     static constexpr int A_BYTES = 128 * 128;           // 128 rows x 64 bf16
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int SMEM = 1024 + LGL_STAGES * STAGE + 256;
+    static constexpr int SMEM = 1024 + LGL_STAGES * STAGE + 256 + (BN == 512 ? 4 * 128 * 4 : 0);
 };
 
+// threads: warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue.  BN = 256 kernels run 2 CTAs per SM with 4 epilogue warps
+// each; the BN = 512 kernel (FC1) fills the SM alone and uses 8 epilogue warps, group g owning columns [256 g, 256 g + 256).
+#define LGL_THREADS(BN) ((BN) == 512 ? 384 : 256)
 template <int MODE, int KIN, int BN>
-__global__ void __launch_bounds__(256, (BN == 256 ? 2 : 1))
+__global__ void __launch_bounds__(LGL_THREADS(BN), (BN == 256 ? 2 : 1))
 lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const int* __restrict__ kp_count,
                  LgPairs pr, int k_cap, const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                  int rotary, const float* __restrict__ cs, bf16* __restrict__ out0, bf16* __restrict__ out1, bf16* __restrict__ out2,
@@ -124,6 +127,7 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* empty = bars + 2;            // [2]
     uint64_t* acc_full = bars + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    float* s_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // FC1: [2 stats][2 groups][128 rows]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&map_a);
@@ -181,21 +185,25 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const size_t tok = (size_t)slot * k_cap + row;
         if (ok) {
             if (MODE == LG_FC1) {
-                // LayerNorm over the 512 outputs of this token: mean, then variance about the mean, then
-                // normalise + exact GELU -> bf16 hidden activation.  Three sweeps over the TMEM-resident row.
+                // LayerNorm over the 512 outputs of this token: mean, then variance about the mean, then normalise +
+                // exact GELU -> bf16 hidden activation.  Three sweeps over the TMEM-resident row; the two column groups
+                // exchange their partial statistics through shared memory.
+                const int grp = (warp - 4) >> 2, cb = grp * (BN / 2), ce = cb + BN / 2;
                 float sum = 0.f;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t r[32];
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]) + __ldg(&bias[c0 + i]);
                 }
-                const float mean = sum * (1.0f / BN);
+                s_stat[grp * 128 + m] = sum;
+                tc::named_bar_sync(1, 256);
+                const float mean = (s_stat[m] + s_stat[128 + m]) * (1.0f / BN);
                 float var = 0.f;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t r[32];
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
@@ -205,9 +213,11 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         var = fmaf(d, d, var);
                     }
                 }
-                const float rstd = rsqrtf(var * (1.0f / BN) + 1e-5f);
+                s_stat[256 + grp * 128 + m] = var;
+                tc::named_bar_sync(1, 256);
+                const float rstd = rsqrtf((s_stat[256 + m] + s_stat[384 + m]) * (1.0f / BN) + 1e-5f);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t r[32];
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
@@ -306,9 +316,10 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #define LGA_K_BYTES (128 * 128)
 #define LGA_V_BYTES (2 * 64 * 128)       // two 64-key chunks of [64 dims][128 B]
 #define LGA_P_BYTES (2 * 128 * 128)      // two 64-key chunks of [128 queries][128 B]
-#define LGA_SMEM (1024 + LGA_Q_BYTES + 2 * LGA_K_BYTES + 2 * LGA_V_BYTES + 2 * LGA_P_BYTES + 256)
+#define LGA_SMEM (1024 + LGA_Q_BYTES + 2 * LGA_K_BYTES + 2 * LGA_V_BYTES + 2 * LGA_P_BYTES + 256 + 4 * 128 * 4)
+#define LGA_THREADS 384   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 softmax
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(LGA_THREADS, 1)
 lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_vt,
                const int* __restrict__ kp_count, LgPairs pr, int k_cap, int cross, bf16* __restrict__ att, int* err) {
     int slot, partner;
@@ -339,6 +350,8 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t* p_empty = bars + 15;      // [2]
     uint64_t* o_full = bars + 17;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    float* s_mx = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][128] per-group row max
+    float* s_sm = s_mx + 256;                                                          // [2][128] per-group row sum
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&map_q);
@@ -349,8 +362,8 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
             tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 4);
-            tc::mbar_init(&p_full[s], 4); tc::mbar_init(&p_empty[s], 1);
+            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 8);
+            tc::mbar_init(&p_full[s], 8); tc::mbar_init(&p_empty[s], 1);
         }
         tc::fence_barrier_init();
     }
@@ -423,53 +436,63 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
+        // ===== softmax: 8 warps; thread <-> query row (TMEM lane), group `grp` owns key columns [64 grp, 64 grp + 64)
+        // of every 128-key tile, i.e. one 64-key chunk of the P operand =====
         const int qd = warp & 3, m = qd * 32 + lane, row = r0 + m;
-        float run_max = -INFINITY, run_sum = 0.f, lse = 0.f;
+        const int grp = (warp - 4) >> 2;
+        const float LOG2E = 1.4426950408889634f;
+        float run_max = -INFINITY, run_sum = 0.f, neg_ml2 = 0.f;
         bool ok = true;
         for (int it = 0; ok && it < total; ++it) {
-            const int pass = it >= nt, j = pass ? it - nt : it, s = it & 1, c0 = j * 128;
-            if (it == nt) lse = run_max + logf(run_sum);
+            const int pass = it >= nt, j = pass ? it - nt : it, s = it & 1, c0 = j * 128 + grp * 64;
+            if (it == nt) {
+                // row max over all keys = max of the two groups' halves
+                s_mx[grp * 128 + m] = run_max;
+                tc::named_bar_sync(1, 256);
+                neg_ml2 = -fmaxf(s_mx[m], s_mx[128 + m]) * LOG2E;
+            }
             if (!tc::mbar_wait(&s_full[s], (it >> 1) & 1, err, 518)) { ok = false; break; }
             const int jb = j & 1;
             if (pass && j >= 2 && !tc::mbar_wait(&p_empty[jb], ((j >> 1) & 1) ^ 1, err, 519)) { ok = false; break; }
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(s * 128);
-#pragma unroll 1
-            for (int cc = 0; cc < 128; cc += 32) {
-                uint32_t v[32];
-                tc::tmem_ld32(taddr + cc, v);
-                tc::tmem_ld_wait();
-                if (!pass) {
-                    float mx = -INFINITY;
+            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(s * 128 + grp * 64);
+            uint32_t v[64];
+            tc::tmem_ld32(taddr, v);
+            tc::tmem_ld32(taddr + 32, v + 32);
+            tc::tmem_ld_wait();
+            const bool full = c0 + 64 <= n_kv;
+            if (!pass) {
+                if (full) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c0 + cc + i < n_kv) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    if (mx > -INFINITY) {
-                        const float nm = fmaxf(run_max, mx);
-                        float e = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c0 + cc + i < n_kv) e += __expf(__uint_as_float(v[i]) - nm);
-                        run_sum = (run_max > -INFINITY ? run_sum * __expf(run_max - nm) : 0.f) + e;
-                        run_max = nm;
-                    }
+                    for (int i = 0; i < 64; ++i) run_max = fmaxf(run_max, __uint_as_float(v[i]));
                 } else {
-                    // P = exp(S - lse) as the bf16 A operand of the second MMA: 64-key chunk (cc >> 6), 16-byte pieces
-                    uint8_t* prow = sP + jb * LGA_P_BYTES + (cc >> 6) * (128 * 128) + m * 128;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = g * 8 + u * 2;
-                            const float p0 = (c0 + cc + i < n_kv) ? __expf(__uint_as_float(v[i]) - lse) : 0.f;
-                            const float p1 = (c0 + cc + i + 1 < n_kv) ? __expf(__uint_as_float(v[i + 1]) - lse) : 0.f;
-                            pk[u] = tc::pack_bf16x2(p0, p1);
-                        }
-                        const int piece = ((cc & 63) >> 3) + g;
-                        *reinterpret_cast<uint4*>(prow + ((piece ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    }
+                    for (int i = 0; i < 64; ++i)
+                        if (c0 + i < n_kv) run_max = fmaxf(run_max, __uint_as_float(v[i]));
                 }
+            } else {
+                // P = exp(S - rowmax) (unnormalised, <= 1) as the bf16 A operand of the second MMA; the row sum of the
+                // unrounded values normalises O at the end
+                float p[64];
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(v[i]), LOG2E, neg_ml2)));
+                    p[i] = e;
+                }
+                if (!full) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        if (c0 + i >= n_kv) p[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 64; ++i) run_sum += p[i];
+                uint8_t* prow = sP + jb * LGA_P_BYTES + grp * (128 * 128) + m * 128;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<uint4*>(prow + ((g ^ (m & 7)) << 4)) =
+                        make_uint4(tc::pack_bf16x2(p[8 * g], p[8 * g + 1]), tc::pack_bf16x2(p[8 * g + 2], p[8 * g + 3]),
+                                   tc::pack_bf16x2(p[8 * g + 4], p[8 * g + 5]), tc::pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
             }
             tc::tc_fence_before();
             if (pass) tc::fence_proxy_async_smem();
@@ -479,24 +502,25 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 if (pass) tc::mbar_arrive(&p_full[jb]);
             }
         }
+        s_sm[grp * 128 + m] = run_sum;
+        tc::named_bar_sync(2, 256);
+        const float inv = __fdiv_rn(1.0f, s_sm[m] + s_sm[128 + m]);
         if (ok && tc::mbar_wait(o_full, 0, err, 520)) {
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u;
-#pragma unroll 1
-            for (int cc = 0; cc < LG_HD; cc += 32) {
-                uint32_t v[32];
-                tc::tmem_ld32(taddr + cc, v);
-                tc::tmem_ld_wait();
-                if (row < n_q) {
-                    bf16* dst = att + ((size_t)slot * k_cap + row) * LG_DIM + head * LG_HD + cc;
+            // O is 64 columns wide: group g converts columns [32 g, 32 g + 32)
+            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(grp * 32);
+            uint32_t v[32];
+            tc::tmem_ld32(taddr, v);
+            tc::tmem_ld_wait();
+            if (row < n_q) {
+                bf16* dst = att + ((size_t)slot * k_cap + row) * LG_DIM + head * LG_HD + grp * 32;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        reinterpret_cast<uint4*>(dst)[g] = make_uint4(
-                            tc::pack_bf16x2(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
-                            tc::pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                            tc::pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                            tc::pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                }
+                for (int g = 0; g < 4; ++g)
+                    reinterpret_cast<uint4*>(dst)[g] = make_uint4(
+                        tc::pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
+                        tc::pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
+                        tc::pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
+                        tc::pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
             }
         }
         tc::tc_fence_before();
@@ -652,11 +676,11 @@ int gnb_lightglue_forward(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, flo
             const LgBlockW& w = st->blocks[2 * l + blk];
             GNB_KERNEL(ctx, "lg_linear<qkv>", lg_linear_kernel<LG_QKV, 256, 256><<<dim3(rt, 3, z), 256, LglCfg<256>::SMEM, ctx->stream>>>(
                 st->m_x, w.m_qkv, ctx->kp_count, pr, kc, w.bqkv, nullptr, nullptr, blk == 0, st->cs, st->q, st->k, st->vt, nullptr, err));
-            GNB_KERNEL(ctx, blk == 0 ? "lg_attn<self>" : "lg_attn<cross>", lg_attn_kernel<<<dim3(rt, LG_HEADS, z), 256, LGA_SMEM, ctx->stream>>>(
+            GNB_KERNEL(ctx, blk == 0 ? "lg_attn<self>" : "lg_attn<cross>", lg_attn_kernel<<<dim3(rt, LG_HEADS, z), LGA_THREADS, LGA_SMEM, ctx->stream>>>(
                 st->m_q, st->m_k, st->m_vt, ctx->kp_count, pr, kc, blk, st->att, err));
             GNB_KERNEL(ctx, "lg_linear<out>", lg_linear_kernel<LG_OUT, 256, 256><<<dim3(rt, 1, z), 256, LglCfg<256>::SMEM, ctx->stream>>>(
                 st->m_att, w.m_o, ctx->kp_count, pr, kc, w.bo, nullptr, nullptr, 0, nullptr, st->xo, nullptr, nullptr, nullptr, err));
-            GNB_KERNEL(ctx, "lg_linear<fc1>", lg_linear_kernel<LG_FC1, 512, 512><<<dim3(rt, 1, z), 256, LglCfg<512>::SMEM, ctx->stream>>>(
+            GNB_KERNEL(ctx, "lg_linear<fc1>", lg_linear_kernel<LG_FC1, 512, 512><<<dim3(rt, 1, z), LGL_THREADS(512), LglCfg<512>::SMEM, ctx->stream>>>(
                 st->m_xo, w.m_w1, ctx->kp_count, pr, kc, w.b1, w.lng, w.lnb, 0, nullptr, st->h, nullptr, nullptr, nullptr, err));
             GNB_KERNEL(ctx, "lg_linear<fc2>", lg_linear_kernel<LG_FC2, 512, 256><<<dim3(rt, 1, z), 256, LglCfg<256>::SMEM, ctx->stream>>>(
                 st->m_h, w.m_w2, ctx->kp_count, pr, kc, w.b2, nullptr, nullptr, 0, nullptr, st->xo, nullptr, nullptr, ctx->desc_f32, err));

@@ -16,7 +16,7 @@ angles, repeated pairwise to the 64-wide head.  Per layer and image:
     cross: q = Linear_q(x), k,v = Linear_k,v(x_other) (no rotation), same MLP pattern with its own weights.
 
 Numerics contract with the CUDA path (``emulate_bf16=True``): tensor-core operands are bf16 — x as a
-GEMM input, q/k/v, the softmax probabilities, the attention output, Wo's output and the MLP hidden
+GEMM input, q/k/v, the unnormalised softmax weights exp(s - max), the attention output, Wo's output and the MLP hidden
 activation — while the residual stream, all accumulations, the softmax statistics, LayerNorm and GELU
 are fp32.  With ``emulate_bf16=False`` everything is fp32 (the form pinned against transformers).
 """
@@ -72,8 +72,11 @@ def _attention(qh, kh, vh, q):
     kh = kh.view(m, HEADS, HEAD_DIM).transpose(0, 1)
     vh = vh.view(m, HEADS, HEAD_DIM).transpose(0, 1)
     s = qh @ kh.transpose(1, 2)
-    p = q(F.softmax(s, dim=-1))
-    return (p @ vh).transpose(0, 1).reshape(n, DIM)
+    # softmax with deferred normalisation (what the CUDA kernel does): the bf16 MMA operand is exp(s - max),
+    # the fp32 row sum of the unrounded values divides the result; identical to softmax(s) @ v in exact arithmetic
+    p = torch.exp(s - s.max(dim=-1, keepdim=True).values)
+    z = p.sum(dim=-1, keepdim=True)
+    return ((q(p) @ vh) / z).transpose(0, 1).reshape(n, DIM)
 
 
 def _block(x, x_kv, p, prefix, q, rot=None, rot_kv=None):

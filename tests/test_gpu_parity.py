@@ -638,3 +638,28 @@ def test_lightglue_matcher_end_to_end(rand_blob, rand_params):
     sc2, idx2 = km.match_arrays(a, b)
     np.testing.assert_array_equal(idx2, base_idx)
     ctx.close()
+
+
+def test_lightglue_layers_in_the_batch_path():
+    """Fused batch path with transformer layers at the reference's depth: residual-zero layers must reproduce the
+    head-only poses exactly (same matches), and random layers must run clean at K = 1024 on every pair."""
+    ground = synth.ground_texture(2048, seed=31, n_shapes=1200)
+    pairs = [synth.make_pair(ground, s, frame_hw=(480, 640), tile_size=512) for s in range(3)]
+    frames, tiles = np.stack([p.frame for p in pairs]), np.stack([p.tile for p in pairs])
+    dems, ks, affs = np.stack([p.dem for p in pairs]), np.stack([p.k for p in pairs]), np.stack([p.affine for p in pairs])
+    ctx = Context(Config(max_batch=3, max_image_h=512, max_image_w=640, max_keypoints=1024))
+    pe = PoseEstimator(ctx)
+    base = pe.estimate_batch(frames, tiles, dems, ks, affs)
+    assert all(r.ok for r in base)
+    ctx.set_matcher_layers(W.pack_layers(W.layers_random_init(9, seed=0, residual_zero=True), 9))
+    l0 = ctx.launch_count
+    with_layers = pe.estimate_batch(frames, tiles, dems, ks, affs)
+    assert ctx.launch_count - l0 >= 9 * 10   # ten launches per layer really ran
+    for a, b in zip(base, with_layers):
+        assert b.ok and a.n_matches == b.n_matches and a.n_inliers == b.n_inliers
+        np.testing.assert_array_equal(a.r, b.r)
+        np.testing.assert_array_equal(a.t, b.t)
+    ctx.set_matcher_layers(W.pack_layers(W.layers_random_init(9, seed=3), 9))
+    rnd = pe.estimate_batch(frames, tiles, dems, ks, affs)   # untrained random layers: statuses are soft failures at worst
+    assert all(r.status >= 0 and r.n_kp_qry > 0 for r in rnd)
+    ctx.close()
