@@ -255,10 +255,17 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             if (rotary) {
                                 // columns c0..c0+31 of a 64-wide head: pairs (2i, 2i+1) share angle i
                                 const int i0 = (c0 & 63) >> 1;
-                                const float* cst = cs + tok * 64;
+                                const float4* cst = reinterpret_cast<const float4*>(cs + tok * 64 + i0);
+                                float cv[16], sv[16];
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const float4 c4 = __ldg(&cst[g]), s4 = __ldg(&cst[8 + g]);
+                                    cv[4 * g] = c4.x; cv[4 * g + 1] = c4.y; cv[4 * g + 2] = c4.z; cv[4 * g + 3] = c4.w;
+                                    sv[4 * g] = s4.x; sv[4 * g + 1] = s4.y; sv[4 * g + 2] = s4.z; sv[4 * g + 3] = s4.w;
+                                }
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
-                                    const float c = __ldg(&cst[i0 + i]), s = __ldg(&cst[32 + i0 + i]);
+                                    const float c = cv[i], s = sv[i];
                                     const float e = v[2 * i], o = v[2 * i + 1];
                                     v[2 * i] = __fadd_rn(__fmul_rn(e, c), __fmul_rn(-o, s));
                                     v[2 * i + 1] = __fadd_rn(__fmul_rn(o, c), __fmul_rn(e, s));
@@ -380,12 +387,12 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tc::tma_load_3d(sQ, &map_q, q_full, head * LG_HD, r0, slot);
             for (int it = 0; it < total; ++it) {
                 const int j = it >= nt ? it - nt : it, s = it & 1;
-                if (it >= 2 && !tc::mbar_wait(&k_empty[s], ((it >> 1) & 1) ^ 1, err, 511)) break;
+                if (it >= 2 && !tc::mbar_wait_fast(&k_empty[s], ((it >> 1) & 1) ^ 1, err, 511)) break;
                 tc::mbar_arrive_expect_tx(&k_full[s], LGA_K_BYTES);
                 tc::tma_load_3d(sK + s * LGA_K_BYTES, &map_k, &k_full[s], head * LG_HD, j * 128, slot_kv);
                 if (it >= nt) {
                     const int sv = j & 1;
-                    if (j >= 2 && !tc::mbar_wait(&v_empty[sv], ((j >> 1) & 1) ^ 1, err, 512)) break;
+                    if (j >= 2 && !tc::mbar_wait_fast(&v_empty[sv], ((j >> 1) & 1) ^ 1, err, 512)) break;
                     tc::mbar_arrive_expect_tx(&v_full[sv], LGA_V_BYTES);
                     tc::tma_load_3d(sV + sv * LGA_V_BYTES, &map_vt, &v_full[sv], j * 128, 0, slot_kv * LG_HEADS + head);
                     tc::tma_load_3d(sV + sv * LGA_V_BYTES + 64 * 128, &map_vt, &v_full[sv], j * 128 + 64, 0, slot_kv * LG_HEADS + head);
@@ -394,14 +401,14 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
     } else if (warp == 1) {
         const uint32_t idesc_s = tc::make_idesc_bf16(128, 128), idesc_o = tc::make_idesc_bf16(128, 64);
-        bool ok = tc::mbar_wait(q_full, 0, err, 513);
+        bool ok = tc::mbar_wait_fast(q_full, 0, err, 513);
         const uint64_t dq = tc::make_smem_desc_sw128(tc::smem_u32(sQ), 1024);
         // software pipeline: S(it) is issued before P V(it - 1), so the softmax warps always have a tile to chew on
         for (int it = 0; ok && it <= total; ++it) {
             if (it < total) {
                 const int s = it & 1;
-                if (!tc::mbar_wait(&k_full[s], (it >> 1) & 1, err, 514)) break;
-                if (it >= 2 && !tc::mbar_wait(&s_empty[s], ((it >> 1) & 1) ^ 1, err, 515)) break;
+                if (!tc::mbar_wait_fast(&k_full[s], (it >> 1) & 1, err, 514)) break;
+                if (it >= 2 && !tc::mbar_wait_fast(&s_empty[s], ((it >> 1) & 1) ^ 1, err, 515)) break;
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
                     const uint64_t dk = tc::make_smem_desc_sw128(tc::smem_u32(sK + s * LGA_K_BYTES), 1024);
@@ -416,8 +423,8 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const int pit = it - 1;
             if (pit >= nt) {
                 const int j = pit - nt, jb = j & 1;
-                if (!tc::mbar_wait(&p_full[jb], (j >> 1) & 1, err, 516)) break;
-                if (!tc::mbar_wait(&v_full[jb], (j >> 1) & 1, err, 517)) break;
+                if (!tc::mbar_wait_fast(&p_full[jb], (j >> 1) & 1, err, 516)) break;
+                if (!tc::mbar_wait_fast(&v_full[jb], (j >> 1) & 1, err, 517)) break;
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
                     const uint64_t dp = tc::make_smem_desc_sw128(tc::smem_u32(sP + jb * LGA_P_BYTES), 1024);
@@ -451,9 +458,9 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 tc::named_bar_sync(1, 256);
                 neg_ml2 = -fmaxf(s_mx[m], s_mx[128 + m]) * LOG2E;
             }
-            if (!tc::mbar_wait(&s_full[s], (it >> 1) & 1, err, 518)) { ok = false; break; }
+            if (!tc::mbar_wait_fast(&s_full[s], (it >> 1) & 1, err, 518)) { ok = false; break; }
             const int jb = j & 1;
-            if (pass && j >= 2 && !tc::mbar_wait(&p_empty[jb], ((j >> 1) & 1) ^ 1, err, 519)) { ok = false; break; }
+            if (pass && j >= 2 && !tc::mbar_wait_fast(&p_empty[jb], ((j >> 1) & 1) ^ 1, err, 519)) { ok = false; break; }
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(s * 128 + grp * 64);
             uint32_t v[64];
@@ -505,7 +512,7 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         s_sm[grp * 128 + m] = run_sum;
         tc::named_bar_sync(2, 256);
         const float inv = __fdiv_rn(1.0f, s_sm[m] + s_sm[128 + m]);
-        if (ok && tc::mbar_wait(o_full, 0, err, 520)) {
+        if (ok && tc::mbar_wait_fast(o_full, 0, err, 520)) {
             tc::tc_fence_after();
             // O is 64 columns wide: group g converts columns [32 g, 32 g + 32)
             const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(grp * 32);

@@ -55,6 +55,32 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
     return true;
 }
 
+// Latency-critical variant: plain try_wait (default, short hardware suspend) in a tight loop.  For hand-offs that
+// sit on a kernel's critical path many times per CTA (attention: S ready -> softmax -> P ready -> MMA).
+__device__ __forceinline__ uint32_t mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ bool mbar_wait_fast(uint64_t* bar, uint32_t parity, volatile int* err, int code) {
+    if (mbar_try_wait_nohint(bar, parity)) return true;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_nohint(bar, parity)) {
+        if (((++spins) & 255u) == 0 && clock64() - t0 > TC_WAIT_TIMEOUT_CYCLES) {
+            if (err) *err = code;
+            return false;
+        }
+    }
+    return true;
+}
+
 // ---- TMA -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
