@@ -9,14 +9,14 @@
 // residual add) then a cross block (same shape, keys/values from the other image, no rotation).
 //
 // Everything dense runs on tcgen05 with bf16 operands and fp32 TMEM accumulators:
-//   lg_linear_kernel<MODE>  Y = A W^T + b: A [tokens][K] and W [N][K] staged by TMA in 64-wide K
-//                           chunks (128B swizzle) through a 2-stage ring; the epilogue (one token row
-//                           per thread, tcgen05.ld) is specialised per use:
+//   lg_linear_persist_kernel<MODE>  Y = A W^T + b with the weight slice resident in shared memory and the
+//                           token tiles streamed by TMA (persistent CTAs, two TMEM accumulator stages);
+//                           the epilogue (one token row per thread, tcgen05.ld) is specialised per use:
 //                             QKV  bias, rotary, 1/sqrt(64) folded into q, V written transposed
 //                             OUT  bias -> second half of the MLP input row
-//                             FC1  bias, LayerNorm(512) and exact GELU straight from TMEM (BN = 512 =
-//                                  the whole TMEM width, so the full row is resident)
 //                             FC2  bias + residual add into the fp32 stream, bf16 copy for the next GEMM
+//   lg_linear_kernel<FC1>   one 128-token tile per CTA, all 512 outputs in TMEM (BN = 512 = the whole TMEM
+//                           width): bias, LayerNorm(512) and exact GELU straight from the resident row
 //   lg_attn_kernel          two-pass softmax attention per (128 queries, head): pass 0 takes the row max of
 //                           S = q k^T from TMEM; pass 1 recomputes S, writes P = exp(S - max) as the bf16 A
 //                           operand (128B-swizzled smem) of the second MMA O += P V and keeps the fp32 row
@@ -39,7 +39,7 @@ enum { LG_QKV = 0, LG_OUT = 1, LG_FC1 = 2, LG_FC2 = 3 };
 struct LgBlockW {
     bf16 *wqkv, *wo, *w1, *w2;             // [768][256], [256][256], [512][512], [256][512]
     float *bqkv, *bo, *b1, *lng, *lnb, *b2;
-    CUtensorMap m_qkv, m_o, m_w1, m_w2;    // box {64, 256}
+    CUtensorMap m_qkv, m_o, m_w1, m_w2;    // box {64, 256}; m_w2: box {64, 128} (FC2 runs as two 128-column slices)
 };
 
 struct LgState {
@@ -49,7 +49,7 @@ struct LgState {
     void* wblob;                            // one device allocation holding every weight
     // activations, [slots][K][...]
     bf16 *xo, *q, *k, *vt, *att, *h;
-    float* cs;                              // [slots][K][64]: cos[32], sin[32]
+    float* cs;                              // [slots][64][K]: cos[32], sin[32] rows, token-contiguous
     CUtensorMap m_x, m_xo, m_att, m_h, m_q, m_k, m_vt;
 };
 
@@ -90,8 +90,10 @@ __global__ void __launch_bounds__(256) lg_init_kernel(const float* __restrict__ 
     const float ang = __fadd_rn(__fmul_rn(x, pos.w[lane * 2]), __fmul_rn(y, pos.w[lane * 2 + 1]));
     float s, c;
     sincosf(ang, &s, &c);
-    cs[tok * 64 + lane] = c;
-    cs[tok * 64 + 32 + lane] = s;
+    // transposed table [slot][cos 0..31, sin 0..31][token]: the row-per-thread epilogue of the q/k projection then
+    // reads it with consecutive lanes on consecutive tokens (one wavefront per load)
+    cs[((size_t)slot * 64 + lane) * k_cap + row] = c;
+    cs[((size_t)slot * 64 + 32 + lane) * k_cap + row] = s;
 }
 
 // ---- linear layers ------------------------------------------------------------------------------------------
@@ -100,7 +102,7 @@ template <int BN> struct LglCfg {
     static constexpr int A_BYTES = 128 * 128;           // 128 rows x 64 bf16
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int SMEM = 1024 + LGL_STAGES * STAGE + 256 + (BN == 512 ? 4 * 128 * 4 : 0);
+    static constexpr int SMEM = 1024 + LGL_STAGES * STAGE + 256 + 4 * 128 * 4 + 3 * BN * 4;   // + LN partials + bias/gamma/beta
 };
 
 // threads: warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue.  BN = 256 kernels run 2 CTAs per SM with 4 epilogue warps
@@ -128,6 +130,7 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* acc_full = bars + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
     float* s_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // FC1: [2 stats][2 groups][128 rows]
+    float* s_par = s_stat + 4 * 128;                                                     // [bias | gamma | beta][BN]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&map_a);
@@ -137,6 +140,10 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc::fence_barrier_init();
     }
     if (warp == 2) { tc::tmem_alloc(tmem_slot, BN); tc::tmem_relinquish(); }
+    for (int i = threadIdx.x; i < BN; i += LGL_THREADS(BN)) {
+        s_par[i] = bias[n0 + i];
+        if (MODE == LG_FC1) { s_par[BN + i] = ln_g[i]; s_par[2 * BN + i] = ln_b[i]; }
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -239,76 +246,6 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int g = 0; g < 4; ++g) o[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                     }
                 }
-            } else {
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tc::tmem_ld32(taddr + c0, r);
-                    tc::tmem_ld_wait();
-                    if (!valid) continue;
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __ldg(&bias[n0 + c0 + i]);
-                    if (MODE == LG_QKV) {
-                        const int part = blockIdx.y;   // 0 q, 1 k, 2 v
-                        if (part < 2) {
-                            if (rotary) {
-                                // columns c0..c0+31 of a 64-wide head: pairs (2i, 2i+1) share angle i
-                                const int i0 = (c0 & 63) >> 1;
-                                const float4* cst = reinterpret_cast<const float4*>(cs + tok * 64 + i0);
-                                float cv[16], sv[16];
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const float4 c4 = __ldg(&cst[g]), s4 = __ldg(&cst[8 + g]);
-                                    cv[4 * g] = c4.x; cv[4 * g + 1] = c4.y; cv[4 * g + 2] = c4.z; cv[4 * g + 3] = c4.w;
-                                    sv[4 * g] = s4.x; sv[4 * g + 1] = s4.y; sv[4 * g + 2] = s4.z; sv[4 * g + 3] = s4.w;
-                                }
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    const float c = cv[i], s = sv[i];
-                                    const float e = v[2 * i], o = v[2 * i + 1];
-                                    v[2 * i] = __fadd_rn(__fmul_rn(e, c), __fmul_rn(-o, s));
-                                    v[2 * i + 1] = __fadd_rn(__fmul_rn(o, c), __fmul_rn(e, s));
-                                }
-                            }
-                            const float sc = part == 0 ? 0.125f : 1.0f;   // 1/sqrt(head_dim) folded into q (exact)
-                            bf16* dst = (part == 0 ? out0 : out1) + tok * LG_DIM + c0;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                reinterpret_cast<uint4*>(dst)[g] =
-                                    make_uint4(tc::pack_bf16x2(v[8 * g] * sc, v[8 * g + 1] * sc), tc::pack_bf16x2(v[8 * g + 2] * sc, v[8 * g + 3] * sc),
-                                               tc::pack_bf16x2(v[8 * g + 4] * sc, v[8 * g + 5] * sc), tc::pack_bf16x2(v[8 * g + 6] * sc, v[8 * g + 7] * sc));
-                        } else {
-                            // V transposed: vt[slot][head][d][token]; consecutive lanes = consecutive tokens
-                            bf16* dst = out2 + ((size_t)slot * LG_DIM + c0) * k_cap + row;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) dst[(size_t)i * k_cap] = __float2bfloat16_rn(v[i]);
-                        }
-                    } else if (MODE == LG_OUT) {
-                        bf16* dst = out0 + tok * LG_HID + LG_DIM + c0;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            reinterpret_cast<uint4*>(dst)[g] =
-                                make_uint4(tc::pack_bf16x2(v[8 * g], v[8 * g + 1]), tc::pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                                           tc::pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), tc::pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-                    } else {   // LG_FC2: residual add into the fp32 stream + bf16 copy for the next GEMM
-                        float4* xr = reinterpret_cast<float4*>(xres + tok * LG_DIM + c0);
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            float4 x = xr[g];
-                            x.x = __fadd_rn(x.x, v[4 * g]); x.y = __fadd_rn(x.y, v[4 * g + 1]);
-                            x.z = __fadd_rn(x.z, v[4 * g + 2]); x.w = __fadd_rn(x.w, v[4 * g + 3]);
-                            xr[g] = x;
-                            v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
-                        }
-                        bf16* dst = out0 + tok * LG_HID + c0;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            reinterpret_cast<uint4*>(dst)[g] =
-                                make_uint4(tc::pack_bf16x2(v[8 * g], v[8 * g + 1]), tc::pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                                           tc::pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), tc::pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-                    }
-                }
             }
         }
         tc::tc_fence_before();
@@ -316,6 +253,216 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, BN); }
+}
+
+// ---- persistent, weight-resident linear layers (QKV / OUT / FC2) ---------------------------------------------------
+// The one-tile-per-CTA kernel above re-streams its whole weight slice (128 KB) from L2 for every 128 tokens, which
+// made the N = 256 layers L2-bound.  Here a CTA loads its weight slice ONCE (KIN x BN bf16 = 128 KB, all K chunks
+// resident in the 128B-swizzle layout), then loops over token tiles: only the A tile (16 KB per K chunk, 4-stage TMA
+// ring) moves, two TMEM accumulator stages overlap the epilogue of tile i with the MMAs of tile i + 1, and eight
+// epilogue warps (two column groups) drain the accumulators.  grid = (CTAs per weight slice, slices).
+#define LGP_STAGES 4
+#define LGP_THREADS 384
+template <int KIN, int BN> struct LgpCfg {
+    static constexpr int W_BYTES = KIN * BN * 2;
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int SMEM = 1024 + W_BYTES + LGP_STAGES * A_BYTES + 256 + BN * 4;
+};
+
+template <int MODE, int KIN, int BN>
+__global__ void __launch_bounds__(LGP_THREADS, 1)
+lg_linear_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const int* __restrict__ kp_count,
+                         LgPairs pr, int k_cap, int row_tiles, const float* __restrict__ bias, int rotary, const float* __restrict__ cs,
+                         bf16* __restrict__ out0, bf16* __restrict__ out1, bf16* __restrict__ out2, float* __restrict__ xres, int* err) {
+    typedef LgpCfg<KIN, BN> Cfg;
+    constexpr int NCHUNK = KIN / 64;
+    const int part = blockIdx.y, n0 = part * BN;     // weight slice = output columns [n0, n0 + BN)
+    const int total_tiles = 2 * pr.pairs * row_tiles;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;                              // NCHUNK x [BN rows x 128 B]
+    uint8_t* sA = smem + Cfg::W_BYTES;               // LGP_STAGES x [128 rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + LGP_STAGES * Cfg::A_BYTES);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [BN] bias of this slice
+    uint64_t* w_full = bars;                 // 1
+    uint64_t* a_full = bars + 1;             // [4]
+    uint64_t* a_empty = bars + 5;            // [4]
+    uint64_t* t_full = bars + 9;             // [2]
+    uint64_t* t_empty = bars + 11;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&map_a);
+        tc::tma_prefetch_desc(&map_w);
+        tc::mbar_init(w_full, 1);
+        for (int s = 0; s < LGP_STAGES; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 8); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) { tc::tmem_alloc(tmem_slot, 2 * BN); tc::tmem_relinquish(); }
+    for (int i = threadIdx.x; i < BN; i += LGP_THREADS) s_bias[i] = bias[n0 + i];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // every role walks the same tile sequence and skips the same empty tiles
+    auto tile_info = [&](int t, int& slot, int& r0) -> bool {
+        int partner;
+        lg_slots(pr, t / row_tiles, slot, partner);
+        r0 = (t % row_tiles) * 128;
+        return r0 < max(kp_count[slot], 0) && max(kp_count[partner], 0) > 0;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(w_full, Cfg::W_BYTES);
+            for (int c = 0; c < NCHUNK; ++c) tc::tma_load_3d(sW + c * BN * 128, &map_w, w_full, c * 64, n0, 0);
+            int g = 0;
+            bool ok = true;
+            for (int t = blockIdx.x; ok && t < total_tiles; t += gridDim.x) {
+                int slot, r0;
+                if (!tile_info(t, slot, r0)) continue;
+                for (int c = 0; c < NCHUNK; ++c, ++g) {
+                    const int s = g % LGP_STAGES;
+                    if (g >= LGP_STAGES && !tc::mbar_wait(&a_empty[s], ((g / LGP_STAGES) & 1) ^ 1, err, 531)) { ok = false; break; }
+                    tc::mbar_arrive_expect_tx(&a_full[s], Cfg::A_BYTES);
+                    tc::tma_load_3d(sA + s * Cfg::A_BYTES, &map_a, &a_full[s], c * 64, r0, slot);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = tc::make_idesc_bf16(128, BN);
+        bool ok = tc::mbar_wait(w_full, 0, err, 532);
+        const uint64_t dw0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
+        const uint64_t da00 = tc::make_smem_desc_sw128(tc::smem_u32(sA), 1024);
+        int g = 0, ti = 0;
+        for (int t = blockIdx.x; ok && t < total_tiles; t += gridDim.x) {
+            int slot, r0;
+            if (!tile_info(t, slot, r0)) continue;
+            const int as = ti & 1;
+            if (ti >= 2 && !tc::mbar_wait(&t_empty[as], ((ti >> 1) & 1) ^ 1, err, 533)) break;
+            for (int c = 0; c < NCHUNK; ++c, ++g) {
+                const int s = g % LGP_STAGES;
+                if (!tc::mbar_wait(&a_full[s], (g / LGP_STAGES) & 1, err, 534)) { ok = false; break; }
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_bf16(tmem_base + (uint32_t)(as * BN), da00 + (uint64_t)((s * Cfg::A_BYTES + k * 32) >> 4),
+                                      dw0 + (uint64_t)((c * BN * 128 + k * 32) >> 4), idesc, (c | k) ? 1u : 0u);
+                    tc::umma_commit(&a_empty[s]);
+                    if (c == NCHUNK - 1) tc::umma_commit(&t_full[as]);
+                }
+                __syncwarp();
+            }
+            ++ti;
+        }
+    } else if (warp >= 4) {
+        // Epilogue: thread <-> accumulator row (TMEM lane).  The read-out is latency-bound (two warps per scheduler),
+        // so the next 32-column TMEM load and this group's global operands (residual / rotary table) are in flight
+        // while the current group is converted and stored; the bias comes from shared memory.
+        const int qd = warp & 3, m = qd * 32 + lane, grp = (warp - 4) >> 2;
+        constexpr int NG = BN / 2 / 32;                       // 32-column groups per thread and tile
+        const int cb = grp * (BN / 2);                        // this warpgroup's first column of the slice
+        int ti = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int slot, r0;
+            if (!tile_info(t, slot, r0)) continue;
+            const int as = ti & 1;
+            if (!tc::mbar_wait(&t_full[as], (ti >> 1) & 1, err, 535)) break;
+            tc::tc_fence_after();
+            const int row = r0 + m;
+            const bool valid = row < max(kp_count[slot], 0);
+            const size_t tok = (size_t)slot * k_cap + row;
+            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(as * BN + cb);
+            uint32_t r[2][32];
+            tc::tmem_ld32(taddr, r[0]);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int c0 = cb + 32 * g, gc = n0 + c0;      // column in the slice / global output column
+                // global operands of this group first, so their latency overlaps the TMEM wait
+                float4 xv[8];
+                float cv[16], sv[16];
+                if (MODE == LG_FC2 && valid) {
+                    const float4* xr = reinterpret_cast<const float4*>(xres + tok * LG_DIM + gc);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[j] = xr[j];
+                }
+                if (MODE == LG_QKV && part < 2 && rotary && valid) {
+                    // columns c0..c0+31 of a 64-wide head: pairs (2i, 2i+1) share angle (c0 & 63)/2 + i
+                    const float* ct = cs + ((size_t)slot * 64 + ((c0 & 63) >> 1)) * k_cap + row;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { cv[i] = __ldg(ct + (size_t)i * k_cap); sv[i] = __ldg(ct + (size_t)(32 + i) * k_cap); }
+                }
+                tc::tmem_ld_wait();
+                if (g + 1 < NG) tc::tmem_ld32(taddr + 32 * (g + 1), r[(g + 1) & 1]);
+                if (!valid) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
+                    v[4 * j] = __uint_as_float(r[g & 1][4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(r[g & 1][4 * j + 1]) + bb.y;
+                    v[4 * j + 2] = __uint_as_float(r[g & 1][4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(r[g & 1][4 * j + 3]) + bb.w;
+                }
+                if (MODE == LG_QKV) {
+                    if (part < 2) {      // 0 q, 1 k, 2 v
+                        if (rotary) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float e = v[2 * i], o = v[2 * i + 1];
+                                v[2 * i] = __fadd_rn(__fmul_rn(e, cv[i]), __fmul_rn(-o, sv[i]));
+                                v[2 * i + 1] = __fadd_rn(__fmul_rn(o, cv[i]), __fmul_rn(e, sv[i]));
+                            }
+                        }
+                        const float sc = part == 0 ? 0.125f : 1.0f;   // 1/sqrt(head_dim) folded into q (exact)
+                        bf16* dst = (part == 0 ? out0 : out1) + tok * LG_DIM + c0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            reinterpret_cast<uint4*>(dst)[j] =
+                                make_uint4(tc::pack_bf16x2(v[8 * j] * sc, v[8 * j + 1] * sc), tc::pack_bf16x2(v[8 * j + 2] * sc, v[8 * j + 3] * sc),
+                                           tc::pack_bf16x2(v[8 * j + 4] * sc, v[8 * j + 5] * sc), tc::pack_bf16x2(v[8 * j + 6] * sc, v[8 * j + 7] * sc));
+                    } else {
+                        bf16* dst = out2 + ((size_t)slot * LG_DIM + c0) * k_cap + row;   // V transposed: [slot][channel][token]
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) dst[(size_t)i * k_cap] = __float2bfloat16_rn(v[i]);
+                    }
+                } else if (MODE == LG_OUT) {
+                    bf16* dst = out0 + tok * LG_HID + LG_DIM + gc;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        reinterpret_cast<uint4*>(dst)[j] =
+                            make_uint4(tc::pack_bf16x2(v[8 * j], v[8 * j + 1]), tc::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       tc::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                } else {   // LG_FC2: residual add into the fp32 stream + bf16 copy for the next GEMM
+                    float4* xr = reinterpret_cast<float4*>(xres + tok * LG_DIM + gc);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 x = xv[j];
+                        x.x = __fadd_rn(x.x, v[4 * j]); x.y = __fadd_rn(x.y, v[4 * j + 1]);
+                        x.z = __fadd_rn(x.z, v[4 * j + 2]); x.w = __fadd_rn(x.w, v[4 * j + 3]);
+                        xr[j] = x;
+                        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+                    }
+                    bf16* dst = out0 + tok * LG_HID + gc;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        reinterpret_cast<uint4*>(dst)[j] =
+                            make_uint4(tc::pack_bf16x2(v[8 * j], v[8 * j + 1]), tc::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       tc::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&t_empty[as]);
+            ++ti;
+        }
+        tc::tc_fence_before();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // ---- attention ------------------------------------------------------------------------------------------------
@@ -627,7 +774,8 @@ extern "C" int gnb_set_matcher_layers(gnb_ctx* ctx, const void* blob, size_t nby
         { const uint64_t d[3] = {256, 768, 1}, s[2] = {512, 768 * 512}; rc |= gnb_make_tmap_bf16(ctx, &w.m_qkv, w.wqkv, 3, d, s, box); }
         { const uint64_t d[3] = {256, 256, 1}, s[2] = {512, 256 * 512}; rc |= gnb_make_tmap_bf16(ctx, &w.m_o, w.wo, 3, d, s, box); }
         { const uint64_t d[3] = {512, 512, 1}, s[2] = {1024, 512 * 1024}; rc |= gnb_make_tmap_bf16(ctx, &w.m_w1, w.w1, 3, d, s, box); }
-        { const uint64_t d[3] = {512, 256, 1}, s[2] = {1024, 256 * 1024}; rc |= gnb_make_tmap_bf16(ctx, &w.m_w2, w.w2, 3, d, s, box); }
+        { const uint32_t b2[3] = {64, 128, 1};
+          const uint64_t d[3] = {512, 256, 1}, s[2] = {1024, 256 * 1024}; rc |= gnb_make_tmap_bf16(ctx, &w.m_w2, w.w2, 3, d, s, b2); }
         if (rc) { gnb_lightglue_free(ctx); return GNB_E_CUDA; }
     }
     GNB_CUDA(ctx, cudaMemcpy(st->wblob, img.data(), total, cudaMemcpyHostToDevice));
@@ -658,10 +806,10 @@ extern "C" int gnb_set_matcher_layers(gnb_ctx* ctx, const void* blob, size_t nby
       const uint64_t d[3] = {(uint64_t)kc, 64, slots * LG_HEADS}, s[2] = {(uint64_t)kc * 2, (uint64_t)kc * 64 * 2};
       rc |= gnb_make_tmap_bf16(ctx, &st->m_vt, st->vt, 3, d, s, bv); }
     if (rc) { gnb_lightglue_free(ctx); return GNB_E_CUDA; }
-    GNB_CUDA(ctx, cudaFuncSetAttribute(lg_linear_kernel<LG_QKV, 256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LglCfg<256>::SMEM));
-    GNB_CUDA(ctx, cudaFuncSetAttribute(lg_linear_kernel<LG_OUT, 256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LglCfg<256>::SMEM));
+    GNB_CUDA(ctx, cudaFuncSetAttribute(lg_linear_persist_kernel<LG_QKV, 256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LgpCfg<256, 256>::SMEM));
+    GNB_CUDA(ctx, cudaFuncSetAttribute(lg_linear_persist_kernel<LG_OUT, 256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LgpCfg<256, 256>::SMEM));
     GNB_CUDA(ctx, cudaFuncSetAttribute(lg_linear_kernel<LG_FC1, 512, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, LglCfg<512>::SMEM));
-    GNB_CUDA(ctx, cudaFuncSetAttribute(lg_linear_kernel<LG_FC2, 512, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LglCfg<256>::SMEM));
+    GNB_CUDA(ctx, cudaFuncSetAttribute(lg_linear_persist_kernel<LG_FC2, 512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, LgpCfg<512, 128>::SMEM));
     GNB_CUDA(ctx, cudaFuncSetAttribute(lg_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LGA_SMEM));
     return GNB_OK;
 }
@@ -676,21 +824,24 @@ int gnb_lightglue_forward(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, flo
     LgPos pos;
     memcpy(pos.w, st->pos_w, sizeof(pos.w));
     const int rt = ceil_div(kc, 128), z = 2 * pairs;
+    // persistent linear kernels: CTAs per weight slice (the slices of one launch share the SMs)
+    const int tiles = z * rt, sms = ctx->sm_count;
+    const int cta1 = tiles < sms ? tiles : sms, cta2 = tiles < sms / 2 ? tiles : sms / 2, cta3 = tiles < sms / 3 ? tiles : sms / 3;
     GNB_KERNEL(ctx, "lg_init_kernel", lg_init_kernel<<<dim3(ceil_div(kc, 8), z), 256, 0, ctx->stream>>>(
         ctx->desc_f32, ctx->kp_xy, ctx->kp_count, pr, kc, pos, ha, wa, hb, wb, st->xo, st->cs));
     for (int l = 0; l < st->n_layers; ++l) {
         for (int blk = 0; blk < 2; ++blk) {
             const LgBlockW& w = st->blocks[2 * l + blk];
-            GNB_KERNEL(ctx, "lg_linear<qkv>", lg_linear_kernel<LG_QKV, 256, 256><<<dim3(rt, 3, z), 256, LglCfg<256>::SMEM, ctx->stream>>>(
-                st->m_x, w.m_qkv, ctx->kp_count, pr, kc, w.bqkv, nullptr, nullptr, blk == 0, st->cs, st->q, st->k, st->vt, nullptr, err));
+            GNB_KERNEL(ctx, "lg_linear<qkv>", lg_linear_persist_kernel<LG_QKV, 256, 256><<<dim3(cta3, 3), LGP_THREADS, LgpCfg<256, 256>::SMEM, ctx->stream>>>(
+                st->m_x, w.m_qkv, ctx->kp_count, pr, kc, rt, w.bqkv, blk == 0, st->cs, st->q, st->k, st->vt, nullptr, err));
             GNB_KERNEL(ctx, blk == 0 ? "lg_attn<self>" : "lg_attn<cross>", lg_attn_kernel<<<dim3(rt, LG_HEADS, z), LGA_THREADS, LGA_SMEM, ctx->stream>>>(
                 st->m_q, st->m_k, st->m_vt, ctx->kp_count, pr, kc, blk, st->att, err));
-            GNB_KERNEL(ctx, "lg_linear<out>", lg_linear_kernel<LG_OUT, 256, 256><<<dim3(rt, 1, z), 256, LglCfg<256>::SMEM, ctx->stream>>>(
-                st->m_att, w.m_o, ctx->kp_count, pr, kc, w.bo, nullptr, nullptr, 0, nullptr, st->xo, nullptr, nullptr, nullptr, err));
+            GNB_KERNEL(ctx, "lg_linear<out>", lg_linear_persist_kernel<LG_OUT, 256, 256><<<dim3(cta1, 1), LGP_THREADS, LgpCfg<256, 256>::SMEM, ctx->stream>>>(
+                st->m_att, w.m_o, ctx->kp_count, pr, kc, rt, w.bo, 0, nullptr, st->xo, nullptr, nullptr, nullptr, err));
             GNB_KERNEL(ctx, "lg_linear<fc1>", lg_linear_kernel<LG_FC1, 512, 512><<<dim3(rt, 1, z), LGL_THREADS(512), LglCfg<512>::SMEM, ctx->stream>>>(
                 st->m_xo, w.m_w1, ctx->kp_count, pr, kc, w.b1, w.lng, w.lnb, 0, nullptr, st->h, nullptr, nullptr, nullptr, err));
-            GNB_KERNEL(ctx, "lg_linear<fc2>", lg_linear_kernel<LG_FC2, 512, 256><<<dim3(rt, 1, z), 256, LglCfg<256>::SMEM, ctx->stream>>>(
-                st->m_h, w.m_w2, ctx->kp_count, pr, kc, w.b2, nullptr, nullptr, 0, nullptr, st->xo, nullptr, nullptr, ctx->desc_f32, err));
+            GNB_KERNEL(ctx, "lg_linear<fc2>", lg_linear_persist_kernel<LG_FC2, 512, 128><<<dim3(cta2, 2), LGP_THREADS, LgpCfg<512, 128>::SMEM, ctx->stream>>>(
+                st->m_h, w.m_w2, ctx->kp_count, pr, kc, rt, w.b2, 0, nullptr, st->xo, nullptr, nullptr, ctx->desc_f32, err));
         }
     }
     return GNB_OK;
