@@ -105,8 +105,9 @@ template <int BN> struct LglCfg {
     static constexpr int SMEM = 1024 + LGL_STAGES * STAGE + 256 + 4 * 128 * 4 + 3 * BN * 4;   // + LN partials + bias/gamma/beta
 };
 
-// threads: warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue.  BN = 256 kernels run 2 CTAs per SM with 4 epilogue warps
-// each; the BN = 512 kernel (FC1) fills the SM alone and uses 8 epilogue warps, group g owning columns [256 g, 256 g + 256).
+// One 128-token tile per CTA, weights streamed in 64-wide K chunks.  Only fc1 uses it (MODE = LG_FC1, BN = 512: the
+// LayerNorm needs all 512 outputs of a token in one CTA, and a 512 x 512 weight matrix cannot stay resident).
+// threads: warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 epilogue, group g owning columns [256 g, 256 g + 256).
 #define LGL_THREADS(BN) ((BN) == 512 ? 384 : 256)
 template <int MODE, int KIN, int BN>
 __global__ void __launch_bounds__(LGL_THREADS(BN), (BN == 256 ? 2 : 1))
