@@ -640,8 +640,10 @@ lg_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     for (int i = 0; i < 64; ++i)
                         if (c0 + i >= n_kv) p[i] = 0.f;
                 }
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains instead of one 64-long dependent FADD chain
 #pragma unroll
-                for (int i = 0; i < 64; ++i) run_sum += p[i];
+                for (int i = 0; i < 64; i += 4) { s0 += p[i]; s1 += p[i + 1]; s2 += p[i + 2]; s3 += p[i + 3]; }
+                run_sum += (s0 + s1) + (s2 + s3);
                 uint8_t* prow = sP + jb * LGA_P_BYTES + grp * (128 * 128) + m * 128;
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
