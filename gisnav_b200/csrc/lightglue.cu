@@ -267,7 +267,7 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 template <int KIN, int BN> struct LgpCfg {
     static constexpr int W_BYTES = KIN * BN * 2;
     static constexpr int A_BYTES = 128 * 128;
-    static constexpr int SMEM = 1024 + W_BYTES + LGP_STAGES * A_BYTES + 256 + BN * 4;
+    static constexpr int SMEM = 1024 + W_BYTES + LGP_STAGES * A_BYTES + 256 + BN * 4 + 8 * 4096;   // + one 4 KB staging tile per epilogue warp
 };
 
 template <int MODE, int KIN, int BN>
@@ -286,6 +286,7 @@ lg_linear_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     uint8_t* sA = smem + Cfg::W_BYTES;               // LGP_STAGES x [128 rows x 128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + LGP_STAGES * Cfg::A_BYTES);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [BN] bias of this slice
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + BN);                          // 8 x 4 KB, one per epilogue warp
     uint64_t* w_full = bars;                 // 1
     uint64_t* a_full = bars + 1;             // [4]
     uint64_t* a_empty = bars + 5;            // [4]
@@ -366,6 +367,7 @@ lg_linear_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         // while the current group is converted and stored; the bias comes from shared memory.
         const int qd = warp & 3, m = qd * 32 + lane, grp = (warp - 4) >> 2;
         constexpr int NG = BN / 2 / 32;                       // 32-column groups per thread and tile
+        uint8_t* stg = s_stage + (warp - 4) * 4096;
         const int cb = grp * (BN / 2);                        // this warpgroup's first column of the slice
         int ti = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -374,9 +376,10 @@ lg_linear_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const int as = ti & 1;
             if (!tc::mbar_wait(&t_full[as], (ti >> 1) & 1, err, 535)) break;
             tc::tc_fence_after();
-            const int row = r0 + m;
-            const bool valid = row < max(kp_count[slot], 0);
-            const size_t tok = (size_t)slot * k_cap + row;
+            const int row = r0 + m, n_rows = max(kp_count[slot], 0);
+            const bool valid = row < n_rows;
+            const int wrow0 = r0 + qd * 32;                              // first row of this warp's 32-row band
+            const size_t tok0 = (size_t)slot * k_cap + wrow0;
             const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(as * BN + cb);
             uint32_t r[2][32];
             tc::tmem_ld32(taddr, r[0]);
@@ -386,10 +389,14 @@ lg_linear_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 // global operands of this group first, so their latency overlaps the TMEM wait
                 float4 xv[8];
                 float cv[16], sv[16];
-                if (MODE == LG_FC2 && valid) {
-                    const float4* xr = reinterpret_cast<const float4*>(xres + tok * LG_DIM + gc);
+                if (MODE == LG_FC2) {
+                    // residual in the write-out mapping (8 lanes per 128-byte row segment)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) xv[j] = xr[j];
+                    for (int i = 0; i < 8; ++i) {
+                        const int q = lane + 32 * i, rr = q >> 3, j = q & 7;
+                        xv[i] = (wrow0 + rr < n_rows) ? *reinterpret_cast<const float4*>(xres + (tok0 + rr) * LG_DIM + gc + j * 4)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
                 if (MODE == LG_QKV && part < 2 && rotary && valid) {
                     // columns c0..c0+31 of a 64-wide head: pairs (2i, 2i+1) share angle (c0 & 63)/2 + i
@@ -399,7 +406,6 @@ lg_linear_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 }
                 tc::tmem_ld_wait();
                 if (g + 1 < NG) tc::tmem_ld32(taddr + 32 * (g + 1), r[(g + 1) & 1]);
-                if (!valid) continue;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -407,51 +413,64 @@ lg_linear_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     v[4 * j] = __uint_as_float(r[g & 1][4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(r[g & 1][4 * j + 1]) + bb.y;
                     v[4 * j + 2] = __uint_as_float(r[g & 1][4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(r[g & 1][4 * j + 3]) + bb.w;
                 }
-                if (MODE == LG_QKV) {
-                    if (part < 2) {      // 0 q, 1 k, 2 v
-                        if (rotary) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float e = v[2 * i], o = v[2 * i + 1];
-                                v[2 * i] = __fadd_rn(__fmul_rn(e, cv[i]), __fmul_rn(-o, sv[i]));
-                                v[2 * i + 1] = __fadd_rn(__fmul_rn(o, cv[i]), __fmul_rn(e, sv[i]));
-                            }
-                        }
-                        const float sc = part == 0 ? 0.125f : 1.0f;   // 1/sqrt(head_dim) folded into q (exact)
-                        bf16* dst = (part == 0 ? out0 : out1) + tok * LG_DIM + c0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            reinterpret_cast<uint4*>(dst)[j] =
-                                make_uint4(tc::pack_bf16x2(v[8 * j] * sc, v[8 * j + 1] * sc), tc::pack_bf16x2(v[8 * j + 2] * sc, v[8 * j + 3] * sc),
-                                           tc::pack_bf16x2(v[8 * j + 4] * sc, v[8 * j + 5] * sc), tc::pack_bf16x2(v[8 * j + 6] * sc, v[8 * j + 7] * sc));
-                    } else {
-                        bf16* dst = out2 + ((size_t)slot * LG_DIM + c0) * k_cap + row;   // V transposed: [slot][channel][token]
+                if (MODE == LG_QKV && part == 2) {
+                    // V transposed [slot][channel][token]: consecutive lanes = consecutive tokens, one line per store
+                    if (valid) {
+                        bf16* dst = out2 + ((size_t)slot * LG_DIM + c0) * k_cap + row;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) dst[(size_t)i * k_cap] = __float2bfloat16_rn(v[i]);
                     }
-                } else if (MODE == LG_OUT) {
-                    bf16* dst = out0 + tok * LG_HID + LG_DIM + gc;
+                    continue;
+                }
+                // Row-major outputs go through this warp's 4 KB staging tile ([32 rows][128 B], 16-byte pieces XOR-swizzled
+                // by row) so that one store instruction covers four whole 128-byte row segments instead of 32 scattered
+                // 16-byte pieces (the L1 tag stage takes one cycle per distinct line).
+                if (MODE == LG_FC2) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        reinterpret_cast<uint4*>(dst)[j] =
-                            make_uint4(tc::pack_bf16x2(v[8 * j], v[8 * j + 1]), tc::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                       tc::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-                } else {   // LG_FC2: residual add into the fp32 stream + bf16 copy for the next GEMM
-                    float4* xr = reinterpret_cast<float4*>(xres + tok * LG_DIM + gc);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 x = xv[j];
-                        x.x = __fadd_rn(x.x, v[4 * j]); x.y = __fadd_rn(x.y, v[4 * j + 1]);
-                        x.z = __fadd_rn(x.z, v[4 * j + 2]); x.w = __fadd_rn(x.w, v[4 * j + 3]);
-                        xr[j] = x;
-                        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+                    for (int i = 0; i < 8; ++i) {
+                        const int q = lane + 32 * i, rr = q >> 3, j = q & 7;
+                        const float4 a = *reinterpret_cast<const float4*>(stg + rr * 128 + ((j ^ (rr & 7)) << 4));
+                        if (wrow0 + rr < n_rows) {
+                            float4 x = xv[i];
+                            x.x = __fadd_rn(x.x, a.x); x.y = __fadd_rn(x.y, a.y); x.z = __fadd_rn(x.z, a.z); x.w = __fadd_rn(x.w, a.w);
+                            *reinterpret_cast<float4*>(xres + (tok0 + rr) * LG_DIM + gc + j * 4) = x;
+                            *reinterpret_cast<uint2*>(out0 + (tok0 + rr) * LG_HID + gc + j * 4) = make_uint2(tc::pack_bf16x2(x.x, x.y), tc::pack_bf16x2(x.z, x.w));
+                        }
                     }
-                    bf16* dst = out0 + tok * LG_HID + gc;
+                    __syncwarp();
+                } else {
+                    if (MODE == LG_QKV && rotary) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float e = v[2 * i], o = v[2 * i + 1];
+                            v[2 * i] = __fadd_rn(__fmul_rn(e, cv[i]), __fmul_rn(-o, sv[i]));
+                            v[2 * i + 1] = __fadd_rn(__fmul_rn(o, cv[i]), __fmul_rn(e, sv[i]));
+                        }
+                    }
+                    const float sc = (MODE == LG_QKV && part == 0) ? 0.125f : 1.0f;   // 1/sqrt(head_dim) folded into q (exact)
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        reinterpret_cast<uint4*>(dst)[j] =
-                            make_uint4(tc::pack_bf16x2(v[8 * j], v[8 * j + 1]), tc::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                       tc::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * (g & 1) + j) ^ (lane & 7)) << 4)) =
+                            make_uint4(tc::pack_bf16x2(v[8 * j] * sc, v[8 * j + 1] * sc), tc::pack_bf16x2(v[8 * j + 2] * sc, v[8 * j + 3] * sc),
+                                       tc::pack_bf16x2(v[8 * j + 4] * sc, v[8 * j + 5] * sc), tc::pack_bf16x2(v[8 * j + 6] * sc, v[8 * j + 7] * sc));
+                    if (g & 1) {   // a 64-column panel (128 B per row) is complete
+                        __syncwarp();
+                        const int pc0 = c0 - 32;   // first column of the panel in the slice
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int q = lane + 32 * i, rr = q >> 3, j = q & 7;
+                            if (wrow0 + rr < n_rows) {
+                                bf16* dst = MODE == LG_OUT ? out0 + (tok0 + rr) * LG_HID + LG_DIM + n0 + pc0 + j * 8
+                                                           : (part == 0 ? out0 : out1) + (tok0 + rr) * LG_DIM + pc0 + j * 8;
+                                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((j ^ (rr & 7)) << 4));
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
             }
             tc::tc_fence_before();
