@@ -102,7 +102,7 @@ template <int BN> struct LglCfg {
     static constexpr int A_BYTES = 128 * 128;           // 128 rows x 64 bf16
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int SMEM = 1024 + LGL_STAGES * STAGE + 256 + 4 * 128 * 4 + 3 * BN * 4;   // + LN partials + bias/gamma/beta
+    static constexpr int SMEM = 1024 + LGL_STAGES * STAGE + 256 + 4 * 128 * 4 + 3 * BN * 4 + 8 * 4096;   // + LN partials + bias/gamma/beta + staging
 };
 
 // One 128-token tile per CTA, weights streamed in 64-wide K chunks.  Only fc1 uses it (MODE = LG_FC1, BN = 512: the
@@ -132,6 +132,7 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
     float* s_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // FC1: [2 stats][2 groups][128 rows]
     float* s_par = s_stat + 4 * 128;                                                     // [bias | gamma | beta][BN]
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_par + 3 * BN);                       // 8 x 4 KB, one per epilogue warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&map_a);
@@ -185,12 +186,10 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __syncwarp();
         }
     } else if (warp >= 4) {
-        const int qd = warp & 3, m = qd * 32 + lane, row = r0 + m;
-        const bool valid = row < n;
+        const int qd = warp & 3, m = qd * 32 + lane;
         const bool ok = tc::mbar_wait(acc_full, 0, err, 503);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
-        const size_t tok = (size_t)slot * k_cap + row;
         if (ok) {
             if (MODE == LG_FC1) {
                 // LayerNorm over the 512 outputs of this token: mean, then variance about the mean, then normalise +
@@ -204,7 +203,7 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]) + __ldg(&bias[c0 + i]);
+                    for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]) + s_par[c0 + i];
                 }
                 s_stat[grp * 128 + m] = sum;
                 tc::named_bar_sync(1, 256);
@@ -217,34 +216,48 @@ lg_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float d = __uint_as_float(r[i]) + __ldg(&bias[c0 + i]) - mean;
+                        const float d = __uint_as_float(r[i]) + s_par[c0 + i] - mean;
                         var = fmaf(d, d, var);
                     }
                 }
                 s_stat[256 + grp * 128 + m] = var;
                 tc::named_bar_sync(1, 256);
                 const float rstd = rsqrtf((s_stat[256 + m] + s_stat[384 + m]) * (1.0f / BN) + 1e-5f);
+                // write-out through this warp's 4 KB staging tile: whole 128-byte row segments per 8 lanes
+                uint8_t* stg = s_stage + (warp - 4) * 4096;
+                const int wrow0 = r0 + qd * 32;
+                const size_t tok0 = (size_t)slot * k_cap + wrow0;
 #pragma unroll 1
                 for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t r[32];
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
-                    if (valid) {
-                        uint32_t pk[16];
+                    uint32_t pk[16];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            float v[2];
+                    for (int i = 0; i < 32; i += 2) {
+                        float v[2];
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int c = c0 + i + u;
-                                const float y = (__uint_as_float(r[i + u]) + __ldg(&bias[c]) - mean) * rstd * __ldg(&ln_g[c]) + __ldg(&ln_b[c]);
-                                v[u] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
-                            }
-                            pk[i >> 1] = tc::pack_bf16x2(v[0], v[1]);
+                        for (int u = 0; u < 2; ++u) {
+                            const int c = c0 + i + u;
+                            const float y = (__uint_as_float(r[i + u]) + s_par[c] - mean) * rstd * s_par[BN + c] + s_par[2 * BN + c];
+                            v[u] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
                         }
-                        uint4* o = reinterpret_cast<uint4*>(out0 + tok * LG_HID + c0);
+                        pk[i >> 1] = tc::pack_bf16x2(v[0], v[1]);
+                    }
+                    const int half = (c0 >> 5) & 1;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) o[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * half + g) ^ (lane & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    if (half) {   // a 64-column panel (128 B per row) is complete
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int q = lane + 32 * i, rr = q >> 3, j = q & 7;
+                            if (wrow0 + rr < n)
+                                *reinterpret_cast<uint4*>(out0 + (tok0 + rr) * LG_HID + c0 - 32 + j * 8) =
+                                    *reinterpret_cast<const uint4*>(stg + rr * 128 + ((j ^ (rr & 7)) << 4));
+                        }
+                        __syncwarp();
                     }
                 }
             }
