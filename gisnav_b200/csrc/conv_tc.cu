@@ -367,6 +367,233 @@ static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUten
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant for the Cin = 128 layers (conv3b, conv4a, conv4b, convPa, convDa).
+// A single SM cannot hold the weights of 128 output channels (9 x 2 x 128 x 128 B = 288 KB), so the kernel above
+// runs N = 64 slices, and N = 64 MMAs are bound by shared-memory operand bandwidth (6 KB per 32-cycle instruction).
+// Here two SMs of a TPC form a cluster and issue ONE tcgen05.mma.cta_group::2 of M = 256, N = 128 per (tap, k-step):
+// each CTA contributes its own 128-pixel halo tile as A and HALF of the 128 weight rows as B (144 KB resident per CTA,
+// as before), and receives its 128 pixels x 128 channels in its own TMEM.  Operand traffic per SM drops to 6 KB per
+// 64-cycle instruction (96 B/clk): the MMA runs at the tensor rate instead of the shared-memory rate.
+//   leader (cluster rank 0): MMA issuer.  It waits for its own and the peer's halo box (the peer relays its TMA
+//   completion with a remote mbarrier arrive), and its tcgen05.commit is multicast to the barriers of both CTAs.
+//   both: TMA producer for their own tile / weight half, epilogue for their own accumulator; the peer's epilogue
+//   warps release the accumulator stage on the leader's barrier.
+#define HP_N 128            // output channels per pair-slice
+#define HP_NH 64            // weight rows per CTA
+template <int KCH, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                         const float* __restrict__ bias, int h, int w, int n_img, int cout, int n_slices,
+                         bf16* __restrict__ out_bf, int relu, int pool, int* err) {
+    constexpr int W_TAP_BYTES = HP_NH * 128;
+    constexpr int W_BYTES = 9 * KCH * W_TAP_BYTES;
+    constexpr int TMEM_COLS = 2 * HP_N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * H2_HALO_STRIDE);
+    uint64_t* w_full = bars;
+    uint64_t* a_full = bars + 1;             // [STAGES] own halo box landed
+    uint64_t* a_empty = a_full + STAGES;     // [STAGES] MMAs done reading (multicast commit)
+    uint64_t* t_full = a_empty + STAGES;     // [2] accumulator ready (multicast commit)
+    uint64_t* t_empty = t_full + 2;          // [2] leader only: 4 local + 4 remote epilogue warps
+    uint64_t* pa_full = t_empty + 2;         // [STAGES] leader only: the peer's halo box landed
+    uint64_t* pw_full = pa_full + STAGES;    // leader only: the peer's weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pw_full + 1);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [HP_N]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int tiles_x = (w + H2_TW - 1) / H2_TW, tiles_y = (h + H2_TH - 1) / H2_TH;
+    const int tiles_per_img = tiles_x * tiles_y;
+    const int total = tiles_per_img * n_img;
+    const int tile_pairs = (total + 1) / 2;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int slice = pair % n_slices;
+    const int tp0 = pair / n_slices, tpstride = n_pairs / n_slices;
+    const int ch0 = slice * HP_N;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_in);
+        tc::tma_prefetch_desc(&tmap_w);
+        tc::mbar_init(w_full, 1);
+        tc::mbar_init(pw_full, 1);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); tc::mbar_init(&pa_full[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 8); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc_pair(tmem_slot, TMEM_COLS);
+        tc::tmem_relinquish_pair();
+    }
+    if (threadIdx.x >= 128 && threadIdx.x - 128 < HP_N) s_bias[threadIdx.x - 128] = bias[ch0 + threadIdx.x - 128];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();     // the peer's barriers exist before anything arrives on them remotely
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(w_full, W_BYTES);
+            for (int t = 0; t < 9; ++t)
+                for (int c = 0; c < KCH; ++c)
+                    tc::tma_load_3d(sW + (t * KCH + c) * W_TAP_BYTES, &tmap_w, w_full, c * 64, ch0 + (int)rank * HP_NH, t);
+            int i = 0;
+            for (int tp = tp0; tp < tile_pairs; tp += tpstride) {
+                const int tile = 2 * tp + (int)rank;     // may be == total for the odd tail: the box is then all zero fill
+                const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+                const int y0 = (rem / tiles_x) * H2_TH, x0 = (rem % tiles_x) * H2_TW;
+                bool ok = true;
+                for (int c = 0; c < KCH; ++c, ++i) {
+                    const int s = i % STAGES;
+                    const uint32_t ph = (i / STAGES) & 1;
+                    if (i >= STAGES && !tc::mbar_wait_cluster(&a_empty[s], ph ^ 1, err, 231)) { ok = false; break; }
+                    tc::mbar_arrive_expect_tx(&a_full[s], H2_HALO_BYTES);
+                    tc::tma_load_4d(sA + s * H2_HALO_STRIDE, &tmap_in, &a_full[s], c * 64, x0 - 1, y0 - 1, img);
+                }
+                if (!ok) break;
+            }
+        }
+    } else if (warp == 3 && rank == 1) {
+        // peer relay: tell the leader when this CTA's operands have landed
+        if (lane == 0) {
+            if (tc::mbar_wait(w_full, 0, err, 232)) tc::mbar_arrive_cluster(tc::map_to_cta(pw_full, 0));
+            int i = 0;
+            bool ok = true;
+            for (int tp = tp0; ok && tp < tile_pairs; tp += tpstride) {
+                for (int c = 0; c < KCH; ++c, ++i) {
+                    const int s = i % STAGES;
+                    if (!tc::mbar_wait(&a_full[s], (i / STAGES) & 1, err, 233)) { ok = false; break; }
+                    tc::mbar_arrive_cluster(tc::map_to_cta(&pa_full[s], 0));
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // leader: one elected lane issues the pair-wide MMAs
+        const uint32_t idesc = tc::make_idesc_bf16(256, HP_N);
+        bool ok = tc::mbar_wait(w_full, 0, err, 234) && tc::mbar_wait_cluster(pw_full, 0, err, 235);
+        const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
+        int i = 0, ti = 0;
+        for (int tp = tp0; ok && tp < tile_pairs; tp += tpstride, ++ti) {
+            const int as = ti & 1;
+            if (ti >= 2 && !tc::mbar_wait_cluster(&t_empty[as], ((ti >> 1) & 1) ^ 1, err, 236)) break;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * HP_N);
+#pragma unroll
+            for (int c = 0; c < KCH; ++c, ++i) {
+                const int s = i % STAGES;
+                if (!tc::mbar_wait(&a_full[s], (i / STAGES) & 1, err, 237)) { ok = false; break; }
+                if (!tc::mbar_wait_cluster(&pa_full[s], (i / STAGES) & 1, err, 238)) { ok = false; break; }
+                tc::tc_fence_after();
+                const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
+                            const uint64_t db = db0 + (uint64_t)(((t * KCH + c) * W_TAP_BYTES + k * 32) >> 4);
+                            tc::umma_bf16_pair(d_tmem, da, db, idesc, (c | t | k) ? 1u : 0u);
+                        }
+                    }
+                    tc::umma_commit_pair(&a_empty[s]);
+                    if (c == KCH - 1) tc::umma_commit_pair(&t_full[as]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int yl = 4 * q + (lane >> 3), xl = lane & 7;
+        const uint32_t leader_te[2] = {tc::map_to_cta(&t_empty[0], 0), tc::map_to_cta(&t_empty[1], 0)};
+        int i = 0;
+        for (int tp = tp0; tp < tile_pairs; tp += tpstride, ++i) {
+            const int as = i & 1;
+            const int tile = 2 * tp + (int)rank;
+            const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int y = (rem / tiles_x) * H2_TH + yl, x = (rem % tiles_x) * H2_TW + xl;
+            if (!tc::mbar_wait_cluster(&t_full[as], (i >> 1) & 1, err, 239)) break;
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * HP_N);
+            const bool inside = (tile < total) && (y < h) && (x < w);
+            size_t pix;
+            bool writer;
+            if (pool) {
+                writer = inside && ((xl | yl) & 1) == 0;
+                pix = ((size_t)img * (h / 2) + (y >> 1)) * (size_t)(w / 2) + (x >> 1);
+            } else {
+                writer = inside;
+                pix = ((size_t)img * h + y) * (size_t)w + x;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < HP_N; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(taddr + c0, v);
+                tc::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j4]);
+                    const float a0 = __uint_as_float(v[4 * j4]) + bb.x, a1 = __uint_as_float(v[4 * j4 + 1]) + bb.y;
+                    const float a2 = __uint_as_float(v[4 * j4 + 2]) + bb.z, a3 = __uint_as_float(v[4 * j4 + 3]) + bb.w;
+                    packed[2 * j4] = relu ? tc::pack_bf16x2_relu(a0, a1) : tc::pack_bf16x2(a0, a1);
+                    packed[2 * j4 + 1] = relu ? tc::pack_bf16x2_relu(a2, a3) : tc::pack_bf16x2(a2, a3);
+                }
+                if (pool) {  // max of bf16-rounded values == rounding of the max (monotone)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t u = packed[j];
+                        uint32_t u1 = __shfl_xor_sync(0xffffffffu, u, 1);
+                        __nv_bfloat162 o = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u), *reinterpret_cast<__nv_bfloat162*>(&u1));
+                        u = *reinterpret_cast<uint32_t*>(&o);
+                        uint32_t u8 = __shfl_xor_sync(0xffffffffu, u, 8);
+                        o = __hmax2(o, *reinterpret_cast<__nv_bfloat162*>(&u8));
+                        packed[j] = *reinterpret_cast<uint32_t*>(&o);
+                    }
+                }
+                if (writer) {
+                    uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + ch0 + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(leader_te[as]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();     // neither CTA frees TMEM / exits while the other may still signal it
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int KCH, int STAGES>
+static int launch_conv_tc_halo_pair(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
+                                    bf16* out_bf, int relu, int pool, const char* name) {
+    constexpr int smem = 1024 + 9 * KCH * HP_NH * 128 + STAGES * H2_HALO_STRIDE + 256 + HP_N * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_pair_kernel<KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int n_slices = L.cout_pad / HP_N;
+    const int tile_pairs = (ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n + 1) / 2;
+    int per_slice = (ctx->sm_count / 2) / n_slices;
+    if (per_slice > tile_pairs) per_slice = tile_pairs;
+    if (per_slice < 1) per_slice = 1;
+    const int grid = 2 * per_slice * n_slices;
+    GNB_KERNEL(ctx, name, conv_tc_halo_pair_kernel<KCH, STAGES><<<grid, 256, smem, ctx->stream>>>(
+        tin, tw, L.bias, h, w, n, L.cout, n_slices, out_bf, relu, pool, gnb_tc_err_dev(ctx)));
+    return GNB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // conv1a + conv1b + 2x2 max-pool in ONE kernel.  The 64-channel full-resolution activation
 // (128 B/pixel written and read back = 2/3 of the whole stack's HBM traffic) never leaves the SM:
 //   im2col warps : 3x3 neighbourhood of the u8 image -> bf16 [256 halo rows x K=16] operand (9 taps)
@@ -747,6 +974,9 @@ int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, i
             return launch_conv_tc_halo<64, 1, 4>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
         if (L.cin == 64 && L.cout_pad == 128)
             return launch_conv_tc_halo<128, 1, 3>(ctx, tin, g_wmaps[lid].w128, L, n, h, w, out_bf, relu, pool, kNames[lid]);
+        static const int no_pair = getenv("GNB_CONV_NO_PAIR") ? atoi(getenv("GNB_CONV_NO_PAIR")) : 0;
+        if (L.cin == 128 && !no_pair && (L.cout_pad % HP_N) == 0)   // CTA pairs: M = 256, N = 128 MMAs, half of the weight rows per SM
+            return launch_conv_tc_halo_pair<2, 3>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
         if (L.cin == 128)  // 128 -> 128 / 256: slices of 64 output channels, weights of a slice resident (144 KB)
             return launch_conv_tc_halo<64, 2, 3>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
     }
