@@ -196,7 +196,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->desc_f32, ctx->mproj, ctx->mlogit, ctx->row_lse, ctx->best_val, ctx->best_idx, ctx->match_idx,
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
-                    ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->warp_buf};
+                    ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
@@ -578,6 +578,12 @@ static void cache_copy(gnb_ctx* ctx, int entry, int slot, bool to_cache) {
     };
     cp(ctx->c_kp_xy + (size_t)entry * k * 2, ctx->kp_xy + (size_t)slot * k * 2, k * 2 * sizeof(float));
     cp(ctx->c_kp_count + entry, ctx->kp_count + slot, sizeof(int));
+    if (ctx->lg_state) {
+        // with transformer layers the cacheable part of a raster is what the extractor produced (keypoints + raw
+        // descriptors): the refined features depend on the query it is paired with
+        cp(ctx->c_desc + (size_t)entry * k * 256, ctx->desc_f32 + (size_t)slot * k * 256, k * 256 * sizeof(float));
+        return;
+    }
     cp(ctx->c_mproj + (size_t)entry * k * 256, ctx->mproj + (size_t)slot * k * 256, k * 256 * sizeof(bf16));
     cp(ctx->c_mlogit + (size_t)entry * k, ctx->mlogit + (size_t)slot * k, k * sizeof(float));
 }
@@ -588,11 +594,11 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
     if (!ctx || !frame || !tiles || !k9 || !affine12 || !results || n_tiles < 1) return GNB_E_INVALID;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_tiles > ctx->cfg.max_batch) { GNB_SET_ERR(ctx, "n_tiles %d exceeds max_batch %d", n_tiles, ctx->cfg.max_batch); return GNB_E_CAPACITY; }
-    if (ctx->lg_state) {
-        // with transformer layers the raster features depend on the query they are paired with, so the per-raster
-        // cache of projected descriptors does not apply
-        GNB_SET_ERR(ctx, "candidate search with the raster feature cache runs the head-only matcher; unload the layers first");
-        return GNB_E_INVALID;
+    const bool layers = ctx->lg_state != nullptr;
+    if (layers && !ctx->c_desc) {
+        const size_t cc = ctx->cache_cap, kk = ctx->cfg.max_keypoints;
+        GNB_CUDA(ctx, cudaMalloc((void**)&ctx->c_desc, cc * kk * 256 * sizeof(float)));
+        gnb_cache_clear(ctx);   // entries cached by the head-only path hold projected, not raw, descriptors
     }
     int rc;
     if ((rc = check_image(ctx, hq, wq)) || (rc = check_image(ctx, ht, wt))) return rc;
@@ -630,7 +636,7 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
     if ((rc = gnb_conv_forward(ctx, 1, hq, wq, 0))) return rc;
     if ((rc = gnb_kp_select(ctx, cw.score, 1, hq, wq, 0))) return rc;
     if ((rc = gnb_describe(ctx, 1, hq, wq, 0))) return rc;
-    if ((rc = gnb_match_project(ctx, 0, 1))) return rc;
+    if (!layers && (rc = gnb_match_project(ctx, 0, 1))) return rc;
     // rasters that missed the cache: one compact batch -> slots [sb, sb + m)
     std::vector<int> miss;
     for (int i = 0; i < n_tiles; ++i) if (!hit[i]) miss.push_back(i);
@@ -645,13 +651,28 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
         if (rc) return rc;
         if ((rc = gnb_kp_select(ctx, cw.score, m, ht, wt, sb))) return rc;
         if ((rc = gnb_describe(ctx, m, ht, wt, sb))) return rc;
-        if ((rc = gnb_match_project(ctx, sb, m))) return rc;
+        if (!layers && (rc = gnb_match_project(ctx, sb, m))) return rc;
         for (int j = 0; j < m; ++j) cache_copy(ctx, entry[miss[j]], sb + j, true);
     }
     for (int i = 0; i < n_tiles; ++i) cache_copy(ctx, entry[i], sb + i, false);
     GNB_CUDA(ctx, cudaGetLastError());
-    if ((rc = gnb_match_pairs(ctx, n_tiles, 0, sb, 0))) return rc;
-    if ((rc = gnb_pnp_pairs(ctx, n_tiles, ht, wt, dems ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1, 0))) return rc;
+    int stride_a = 0;
+    if (layers) {
+        // the layers refine the query features against each candidate separately: one copy of the frame per pair
+        // (slots 1..n-1), then layers + head over n ordinary pairs
+        const size_t kk = ctx->cfg.max_keypoints;
+        for (int i = 1; i < n_tiles; ++i) {
+            GNB_CUDA(ctx, cudaMemcpyAsync(ctx->desc_f32 + (size_t)i * kk * 256, ctx->desc_f32, kk * 256 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+            GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_xy + (size_t)i * kk * 2, ctx->kp_xy, kk * 2 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+            GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count + i, ctx->kp_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        if ((rc = gnb_lightglue_forward(ctx, n_tiles, 0, sb, (float)hq, (float)wq, (float)ht, (float)wt))) return rc;
+        if ((rc = gnb_match_project(ctx, 0, n_tiles))) return rc;
+        if ((rc = gnb_match_project(ctx, sb, n_tiles))) return rc;
+        stride_a = 1;
+    }
+    if ((rc = gnb_match_pairs(ctx, n_tiles, 0, sb, stride_a))) return rc;
+    if ((rc = gnb_pnp_pairs(ctx, n_tiles, ht, wt, dems ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1, stride_a))) return rc;
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut) * n_tiles, cudaMemcpyDeviceToHost, ctx->stream));
     GNB_SYNC(ctx);
     for (int b = 0; b < n_tiles; ++b) {

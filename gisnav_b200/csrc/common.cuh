@@ -105,6 +105,7 @@ struct gnb_ctx {
     int* c_kp_count;                // [cache_cap]
     bf16* c_mproj;                  // [cache_cap][K][256]
     float* c_mlogit;                // [cache_cap][K]
+    float* c_desc;                  // [cache_cap][K][256] raw descriptors, allocated with the transformer layers (lightglue.cu)
     uint8_t* warp_buf;              // staging of gnb_rotate_crop's host-buffer path (warp.cu), grow-only
     size_t warp_bytes;
     void* lg_state;                 // LgState* (lightglue.cu): transformer layers in front of the head, NULL = head only

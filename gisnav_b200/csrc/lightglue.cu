@@ -745,6 +745,7 @@ extern "C" int gnb_set_matcher_layers(gnb_ctx* ctx, const void* blob, size_t nby
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     gnb_lightglue_free(ctx);
+    gnb_cache_clear(ctx);                      // cached raster features are specific to the matcher configuration
     if (!blob || nbytes == 0) return GNB_OK;   // back to the head-only matcher
     if (ctx->cfg.match_impl != 0) { GNB_SET_ERR(ctx, "transformer layers need the tcgen05 matcher (match_impl = 0)"); return GNB_E_INVALID; }
     const int kc = ctx->cfg.max_keypoints;

@@ -166,7 +166,8 @@ int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, int hq, int w
  * the device keyed by tile_ids[i] (the reference re-extracts a raster only when its stamp changes,
  * pose_node.py:226-241); id < 0 = never cached; tile_ids NULL = no caching.  tiles u8 [n,ht,wt],
  * dems u8 [n,ht,wt] or NULL, k9 f64 [9], affine12 f64 [n,12].  results: HOST array of n_tiles;
- * n_cache_hits (optional) = rasters whose features came from the cache. */
+ * n_cache_hits (optional) = rasters whose features came from the cache.  With transformer layers loaded the cache
+ * keeps the rasters' raw keypoints + descriptors and the frame is refined against every candidate separately. */
 int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* tiles, int ht,
                         int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9, const double* affine12,
                         gnb_pose_result* results, int* n_cache_hits);

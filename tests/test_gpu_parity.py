@@ -663,3 +663,36 @@ def test_lightglue_layers_in_the_batch_path():
     rnd = pe.estimate_batch(frames, tiles, dems, ks, affs)   # untrained random layers: statuses are soft failures at worst
     assert all(r.status >= 0 and r.n_kp_qry > 0 for r in rnd)
     ctx.close()
+
+
+def test_candidate_search_with_transformer_layers():
+    """Config 4 with the reference matcher's layers loaded: the cache then holds the rasters' RAW features (the refined
+    ones depend on the paired query), the frame is refined once per candidate, and residual-zero layers must give
+    exactly the head-only candidate results — on a cold and on a fully cached call."""
+    blob = _trained_blob()
+    ground = synth.ground_texture(2048, seed=24, n_shapes=3000)
+    ctx = Context(Config(max_batch=4, max_image_h=256, max_image_w=320, max_keypoints=512), weights=blob)
+    pe = PoseEstimator(ctx)
+    pair = synth.make_pair(ground, 1, frame_hw=(240, 320), tile_size=256)
+    decoys = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256).tile for s in (11, 12, 13)]
+    tiles = np.stack([decoys[0], pair.tile, decoys[1], decoys[2]])
+    ids = np.array([100, 101, 102, 103])
+    affines = np.stack([pair.affine] * 4)
+    best0, res0, _ = pe.estimate_candidates(pair.frame, tiles, ids, None, pair.k, affines)          # head only
+    ctx.set_matcher_layers(W.pack_layers(W.layers_random_init(3, seed=2, residual_zero=True), 3))
+    l0 = ctx.launch_count
+    best1, res1, hits1 = pe.estimate_candidates(pair.frame, tiles, ids, None, pair.k, affines)      # cold: cache was reset
+    assert hits1 == 0 and best1 == best0 == 1
+    assert ctx.launch_count - l0 > 3 * 10
+    best2, res2, hits2 = pe.estimate_candidates(pair.frame, tiles, ids, None, pair.k, affines)      # all four cached
+    assert hits2 == 4 and best2 == 1
+    for a, b, c in zip(res0, res1, res2):
+        assert a.status == b.status == c.status and a.n_matches == b.n_matches == c.n_matches
+        assert a.n_inliers == b.n_inliers == c.n_inliers
+        np.testing.assert_array_equal(a.r, b.r)
+        np.testing.assert_array_equal(a.r, c.r)
+    ctx.set_matcher_layers(None)                                                                     # back to the head: cache reset again
+    best3, res3, hits3 = pe.estimate_candidates(pair.frame, tiles, ids, None, pair.k, affines)
+    assert hits3 == 0 and best3 == 1
+    np.testing.assert_array_equal(res3[1].r, res0[1].r)
+    ctx.close()

@@ -153,3 +153,19 @@ def test_crs_string_ingest_matches_reference_parser():
     np.testing.assert_array_equal(tail_ref.proj_to_affine(crs.affine_to_proj(a)), a)
     with pytest.raises(ValueError):
         crs.proj_to_affine("+proj=affine +xoff=1")
+
+
+def test_stereo_host_helpers_match_oracle():
+    """Host-side bookkeeping of StereoAligner (yaw bucket, CRS composition) against the oracle restatement of
+    stereo_node.py:136-168,208-216; the pixel kernel itself is covered by the GPU tests."""
+    from gisnav_b200 import crs, stereo, synth
+    from oracle import stereo_ref
+
+    for yaw, roll in ((0, 0), (22, 0), (23, 0), (67.9, 0), (200, 30), (359.9, 0), (-10, 0), (44, 2), (350, 15)):
+        assert stereo.map_rotation(yaw, roll) == stereo_ref.map_rotation(yaw, roll)
+    a = synth.tile_affine(321.0, 654.0)
+    _, inv = stereo_ref.rotate_and_crop_center(np.zeros((149, 149), np.uint8), 135, (72, 104))
+    got = stereo.world_to_reference_affine(inv, a)
+    np.testing.assert_array_equal(got, stereo_ref.world_to_reference_affine(inv, a))
+    # the composed matrix survives the proj-string round trip the message carries (stereo_node.py:257-260)
+    np.testing.assert_array_equal(crs.proj_to_affine(crs.affine_to_proj(got)), got)
