@@ -507,6 +507,7 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
         const int q = warp & 3;
         const int yl = 4 * q + (lane >> 3), xl = lane & 7;
         const uint32_t leader_te[2] = {tc::map_to_cta(&t_empty[0], 0), tc::map_to_cta(&t_empty[1], 0)};
+        uint8_t* stg = reinterpret_cast<uint8_t*>(s_bias + HP_N) + (warp - 4) * 2048;
         int i = 0;
         for (int tp = tp0; tp < tile_pairs; tp += tpstride, ++i) {
             const int as = i & 1;
@@ -552,10 +553,30 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
                         packed[j] = *reinterpret_cast<uint32_t*>(&o);
                     }
                 }
-                if (writer) {
-                    uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + ch0 + c0);
+                if (pool) {
+                    if (writer) {
+                        uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + ch0 + c0);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                        for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                    }
+                } else {
+                    // full-resolution write-out through this warp's 2 KB staging tile ([32 px][64 B], pieces XOR-swizzled):
+                    // four lanes then store one pixel's 64 contiguous bytes, so an instruction touches 8 lines instead of 32
+                    // (global stores share the L1 / shared-memory data path the MMA operands are fetched through)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+                            make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int it4 = 0; it4 < 4; ++it4) {
+                        const int qq = lane + 32 * it4, pp = qq >> 2, j = qq & 3;
+                        const int py = y - yl + 4 * q + (pp >> 3), px = x - xl + (pp & 7);
+                        if (tile < total && py < h && px < w)
+                            *reinterpret_cast<uint4*>(out_bf + (((size_t)img * h + py) * (size_t)w + px) * cout + ch0 + c0 + j * 8) =
+                                *reinterpret_cast<const uint4*>(stg + pp * 64 + ((j ^ ((pp >> 1) & 3)) << 4));
+                    }
+                    __syncwarp();
                 }
             }
             tc::tc_fence_before();
@@ -575,7 +596,7 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
 template <int KCH, int STAGES>
 static int launch_conv_tc_halo_pair(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
                                     bf16* out_bf, int relu, int pool, const char* name) {
-    constexpr int smem = 1024 + 9 * KCH * HP_NH * 128 + STAGES * H2_HALO_STRIDE + 256 + HP_N * 4;
+    constexpr int smem = 1024 + 9 * KCH * HP_NH * 128 + STAGES * H2_HALO_STRIDE + 256 + HP_N * 4 + 4 * 2048;   // + write-out staging
     static bool attr_set = false;
     if (!attr_set) {
         GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_pair_kernel<KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
