@@ -1,2 +1,1 @@
-mkdir -p gpurun_out
-GNB_ATTN_DEBUG=1 timeout 600 python bench.py --steps 2 --warmup 3 --batch 16 --cpu-pairs 0 --matcher-layers 1 2>&1 | grep _DBG | tail -3
+GNB_ATTN_DEBUG=1 timeout 600 python bench.py --steps 2 --warmup 3 --batch 16 --cpu-pairs 0 --matcher-layers 1 2>&1 | grep FC1_DBG | tail -3
