@@ -182,7 +182,8 @@ template <int NPAD, int KCH, int STAGES>
 __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_in,
                                                               const __grid_constant__ CUtensorMap tmap_w,
                                                               const float* __restrict__ bias, int h, int w, int n_img, int cout,
-                                                              int n_slices, bf16* __restrict__ out_bf, int relu, int pool, int* err) {
+                                                              int n_slices, bf16* __restrict__ out_bf, int relu, int pool, int* err,
+                                                              const __grid_constant__ CUtensorMap tmap_out, int tstore) {
     constexpr int W_TAP_BYTES = NPAD * 128;        // one (tap, chunk) block
     constexpr int W_BYTES = 9 * KCH * W_TAP_BYTES;
     constexpr int TMEM_COLS = 2 * NPAD;  // 128 or 256
@@ -198,6 +199,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     uint64_t* t_empty = t_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [NPAD], 16-byte aligned
+    // tstore: 16 KB staging panel [128 px][64 ch] (128B swizzle) for the TMA write-out, 1024-byte aligned behind the bias
+    uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_bias + NPAD) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (w + H2_TW - 1) / H2_TW, tiles_y = (h + H2_TH - 1) / H2_TH;
@@ -327,7 +330,28 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
                         packed[j] = *reinterpret_cast<uint32_t*>(&o);
                     }
                 }
-                if (writer) {
+                if (tstore) {
+                    // full-resolution write-out by TMA: the tile's 64-channel panel is staged as [128 px][128 B] (pixel m =
+                    // yl * 8 + xl = this thread's TMEM lane) and stored with one bulk tensor copy: whole lines, clipped at
+                    // the image border by the tensor map, and no store instruction competes with the MMA operand fetch
+                    const int m = q * 32 + lane;
+                    if ((c0 & 63) == 0) {
+                        if (threadIdx.x == 128) tc::tma_store_wait_read();   // previous panel has left the staging buffer
+                        tc::named_bar_sync(1, 128);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(sOut + m * 128 + (((((c0 & 63) >> 3) + g) ^ (m & 7)) << 4)) =
+                            make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                    if ((c0 & 63) == 32) {
+                        tc::fence_proxy_async_smem();
+                        tc::named_bar_sync(1, 128);
+                        if (threadIdx.x == 128) {
+                            tc::tma_store_4d(&tmap_out, sOut, ch0 + c0 - 32, x - xl, y - yl, img);
+                            tc::tma_store_commit();
+                        }
+                    }
+                } else if (writer) {
                     uint4* o = reinterpret_cast<uint4*>(out_bf + pix * cout + ch0 + c0);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
@@ -337,6 +361,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&t_empty[as]);
         }
+        if (tstore && threadIdx.x == 128) tc::tma_store_wait_all();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -346,10 +371,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     }
 }
 
-template <int NPAD, int KCH, int STAGES>
+template <int NPAD, int KCH, int STAGES, bool TSTORE = false>
 static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
                                bf16* out_bf, int relu, int pool, const char* name) {
-    constexpr int smem = 1024 + 9 * KCH * NPAD * 128 + STAGES * H2_HALO_STRIDE + 256 + NPAD * 4;
+    constexpr int smem = 1024 + 9 * KCH * NPAD * 128 + STAGES * H2_HALO_STRIDE + 256 + NPAD * 4 + (TSTORE ? 1024 + 16384 : 0);
     static bool attr_set = false;
     if (!attr_set) {
         GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_kernel<NPAD, KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -361,8 +386,17 @@ static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUten
     if (per_slice > total) per_slice = total;
     if (per_slice < 1) per_slice = 1;
     const int grid = per_slice * n_slices;
+    CUtensorMap tout = tin;   // placeholder when the TMA write-out is off
+    const int tstore = (TSTORE && !pool) ? 1 : 0;
+    if (tstore) {
+        const uint64_t od[4] = {(uint64_t)L.cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        const uint64_t os[3] = {(uint64_t)L.cout * 2, (uint64_t)w * L.cout * 2, (uint64_t)h * w * L.cout * 2};
+        const uint32_t ob[4] = {64, H2_TW, H2_TH, 1};
+        int rc = gnb_make_tmap_bf16(ctx, &tout, out_bf, 4, od, os, ob);
+        if (rc) return rc;
+    }
     GNB_KERNEL(ctx, name, conv_tc_halo_kernel<NPAD, KCH, STAGES><<<grid, 256, smem, ctx->stream>>>(
-        tin, tw, L.bias, h, w, n, L.cout, n_slices, out_bf, relu, pool, gnb_tc_err_dev(ctx)));
+        tin, tw, L.bias, h, w, n, L.cout, n_slices, out_bf, relu, pool, gnb_tc_err_dev(ctx), tout, tstore));
     return GNB_OK;
 }
 
@@ -994,7 +1028,7 @@ int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, i
         if (L.cin == 64 && L.cout_pad == 64)
             return launch_conv_tc_halo<64, 1, 4>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
         if (L.cin == 64 && L.cout_pad == 128)
-            return launch_conv_tc_halo<128, 1, 3>(ctx, tin, g_wmaps[lid].w128, L, n, h, w, out_bf, relu, pool, kNames[lid]);
+            return launch_conv_tc_halo<128, 1, 2, true>(ctx, tin, g_wmaps[lid].w128, L, n, h, w, out_bf, relu, pool, kNames[lid]);
         static const int no_pair = getenv("GNB_CONV_NO_PAIR") ? atoi(getenv("GNB_CONV_NO_PAIR")) : 0;
         if (L.cin == 128 && !no_pair && (L.cout_pad % HP_N) == 0)   // CTA pairs: M = 256, N = 128 MMAs, half of the weight rows per SM
             return launch_conv_tc_halo_pair<2, 3>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
