@@ -169,3 +169,28 @@ def test_stereo_host_helpers_match_oracle():
     np.testing.assert_array_equal(got, stereo_ref.world_to_reference_affine(inv, a))
     # the composed matrix survives the proj-string round trip the message carries (stereo_node.py:257-260)
     np.testing.assert_array_equal(crs.proj_to_affine(crs.affine_to_proj(got)), got)
+
+
+def test_layer_blob_roundtrip_and_validation():
+    """GNBL layer blob (transformer layers in front of the matcher head): layout, round trip, rejection of bad blobs."""
+    from gisnav_b200 import weights as W
+
+    n_layers = 2
+    table = W.layer_tensors(n_layers)
+    assert list(table)[0] == "lg.pos.weight" and table["lg.pos.weight"] == (32, 2)
+    assert table["lg.1.cross.fc1.weight"] == (512, 512) and table["lg.0.self.fc2.weight"] == (256, 512)
+    per_block = 4 * (256 * 256 + 256) + 512 * 512 + 3 * 512 + 256 * 512 + 256
+    assert W.layer_floats(n_layers) == 64 + 2 * n_layers * per_block      # what csrc/lightglue.cu expects
+    p = W.layers_random_init(n_layers, seed=5)
+    blob = W.pack_layers(p, n_layers)
+    assert blob[:4] == b"GNBL" and len(blob) == 16 + 4 * W.layer_floats(n_layers)
+    q, n = W.unpack_layers(blob)
+    assert n == n_layers and all(np.array_equal(p[k], q[k]) for k in p)
+    z = W.layers_random_init(n_layers, seed=5, residual_zero=True)
+    assert all(not z[k].any() for k in z if ".fc2." in k) and z["lg.0.self.fc1.weight"].any()
+    for bad in (blob[:-4], b"GNBW" + blob[4:], blob[:4] + (99).to_bytes(4, "little") + blob[8:]):
+        with pytest.raises(ValueError):
+            W.unpack_layers(bad)
+    p["lg.0.self.q.weight"] = np.zeros((255, 256), np.float32)
+    with pytest.raises(ValueError):
+        W.pack_layers(p, n_layers)
