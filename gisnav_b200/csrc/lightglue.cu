@@ -760,8 +760,16 @@ void gnb_lightglue_free(gnb_ctx* ctx) {
 
 extern "C" int gnb_matcher_layers(const gnb_ctx* ctx) { return (ctx && ctx->lg_state) ? lg_state(const_cast<gnb_ctx*>(ctx))->n_layers : 0; }
 
+static int lg_load(gnb_ctx* ctx, const void* blob, size_t nbytes);
+
 extern "C" int gnb_set_matcher_layers(gnb_ctx* ctx, const void* blob, size_t nbytes) {
     if (!ctx) return GNB_E_INVALID;
+    const int rc = lg_load(ctx, blob, nbytes);
+    if (rc != GNB_OK) gnb_lightglue_free(ctx);   // never leave a half-built layer state behind: the matcher falls back to the head
+    return rc;
+}
+
+static int lg_load(gnb_ctx* ctx, const void* blob, size_t nbytes) {
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     gnb_lightglue_free(ctx);

@@ -45,7 +45,8 @@ def oracle():
 
 # ---- K1: dense stack ------------------------------------------------------------------------------
 @pytest.mark.parametrize("impl", IMPLS)
-@pytest.mark.parametrize("hw", [(96, 128), (64, 72), (120, 200)])
+@pytest.mark.parametrize("hw", [(96, 128), (64, 72), (120, 200), (40, 48)])   # (40, 48): a single H/8 tile, i.e. an odd
+# tile count for the CTA-pair kernels (the peer CTA of the last pair runs on a zero-filled dummy tile)
 def test_k1_dense_matches_oracle(rand_blob, rand_params, oracle, impl, hw):
     h, w = hw
     img = np.ascontiguousarray(synth.ground_texture(512, seed=11, n_shapes=300)[40 : 40 + h, 60 : 60 + w])
