@@ -194,3 +194,32 @@ def test_layer_blob_roundtrip_and_validation():
     p["lg.0.self.q.weight"] = np.zeros((255, 256), np.float32)
     with pytest.raises(ValueError):
         W.pack_layers(p, n_layers)
+
+
+def test_stereo_aligner_rotation_cache_semantics():
+    """StereoAligner.pnp_image re-warps the raster only when the 45-degree yaw bucket changes, like StereoNode
+    (stereo_node.py:218-227,262-265).  The pixel kernel is stubbed out: this is host logic only."""
+    from gisnav_b200 import crs, stereo, synth
+    from oracle import stereo_ref
+
+    sa = object.__new__(stereo.StereoAligner)          # no Context: align() is replaced below
+    sa._previous_map_rotation, sa._cached = None, None
+    calls = []
+
+    def fake_align(ortho, dem, angle, shape):
+        calls.append(angle)
+        _, inv = stereo_ref.rotate_and_crop_center(np.zeros(ortho.shape[:2], np.uint8), angle, shape)
+        return np.full(shape, angle % 256, np.uint8), np.zeros(shape, np.uint8), inv
+
+    sa.align = fake_align
+    ortho, dem = np.zeros((149, 149, 3), np.uint8), np.zeros((149, 149), np.uint8)
+    proj = crs.affine_to_proj(synth.tile_affine(10.0, 20.0))
+    out = [sa.pnp_image((72, 104), ortho, dem, proj, yaw) for yaw in (3.0, 20.0, 24.0, 40.0, 80.0, 75.0, 359.0)]
+    # buckets: 0, 0, 45, 45, 90, 90, 0  ->  warps at the first frame and at every bucket change
+    assert calls == [0, 45, 90, 0]
+    assert out[0] is out[1] and out[2] is out[3] and out[4] is out[5]
+    for (ref, _, proj_str), angle in zip((out[0], out[2], out[4]), (0, 45, 90)):
+        assert ref[0, 0] == angle
+        _, inv = stereo_ref.rotate_and_crop_center(np.zeros((149, 149), np.uint8), angle, (72, 104))
+        want = stereo_ref.world_to_reference_affine(inv, crs.proj_to_affine(proj))
+        np.testing.assert_array_equal(crs.proj_to_affine(proj_str), want)
