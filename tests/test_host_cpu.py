@@ -223,3 +223,22 @@ def test_stereo_aligner_rotation_cache_semantics():
         _, inv = stereo_ref.rotate_and_crop_center(np.zeros((149, 149), np.uint8), angle, (72, 104))
         want = stereo_ref.world_to_reference_affine(inv, crs.proj_to_affine(proj))
         np.testing.assert_array_equal(crs.proj_to_affine(proj_str), want)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the B200 arm): one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-pairs", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "matched_frame_pairs_per_sec" and line["unit"] == "pairs/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["config"]["workload"].startswith("config 2")
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["value"] > 0 and line["matched_fraction"] == 1.0
