@@ -358,3 +358,20 @@ def test_lightglue_layers_match_transformers():
     u0, u1 = lightglue_ref.forward(d[0], kp[0], hw, d[1], kp[1], hw, lz, 2)
     np.testing.assert_array_equal(u0, d[0])
     np.testing.assert_array_equal(u1, d[1])
+
+
+def test_nms_survivors_above_a_level_depend_only_on_pixels_above_it():
+    """Lemma behind a future top-K-aware (sparse) NMS kernel, DESIGN.md §10: for any level T, the survivors of
+    simple_nms with score > T are unchanged when every pixel <= T is replaced by 0 — a pixel can only suppress pixels
+    that are not larger than itself.  Checked on maps with plateaus and ties."""
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        if trial % 2 == 0:
+            s = rng.random((96, 120)).astype(np.float32) ** 3
+        else:
+            s = (np.round(rng.random((80, 104)) * 12) / 12).astype(np.float32)     # heavy ties
+            s[20:30, 40:60] = 0.75                                                    # a plateau
+        full = nms_ref.simple_nms(s, 4)
+        for level in (0.005, 0.1, 0.4, 0.74, 0.9):
+            sparse = nms_ref.simple_nms(np.where(s > np.float32(level), s, np.float32(0)), 4)
+            np.testing.assert_array_equal(np.where(full > level, full, 0), np.where(sparse > level, sparse, 0))
