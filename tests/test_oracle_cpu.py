@@ -375,3 +375,22 @@ def test_nms_survivors_above_a_level_depend_only_on_pixels_above_it():
         for level in (0.005, 0.1, 0.4, 0.74, 0.9):
             sparse = nms_ref.simple_nms(np.where(s > np.float32(level), s, np.float32(0)), 4)
             np.testing.assert_array_equal(np.where(full > level, full, 0), np.where(sparse > level, sparse, 0))
+
+
+def test_topk_selection_is_unchanged_by_zeroing_below_a_safe_level():
+    """End-to-end form of the lemma: if at least K survivors lie above level T, the ordered top-K keypoint list is the
+    same whether or not the pixels <= T are zeroed first — the acceptance test of a sparse, top-K-aware NMS."""
+    rng = np.random.default_rng(21)
+    s = (rng.random((160, 200)).astype(np.float32) ** 4) * 0.2
+    k = 60
+    xy_full, sc_full = nms_ref.select_keypoints(s, max_keypoints=k)
+    assert len(xy_full) == k
+    for q in (0.5, 0.8, 0.9):
+        level = np.float32(np.quantile(s, q))
+        xy_all, sc_all = nms_ref.select_keypoints(np.where(s > level, s, np.float32(0)), max_keypoints=-1, threshold=float(level))
+        if len(xy_all) >= k:       # enough survivors above the level: accept
+            np.testing.assert_array_equal(xy_all[:k], xy_full)
+            np.testing.assert_array_equal(sc_all[:k], sc_full)
+        else:                       # too few: a kernel would lower the level and repeat
+            assert sc_full[-1] <= level
+    assert len(nms_ref.select_keypoints(np.where(s > np.quantile(s, 0.5), s, 0).astype(np.float32), max_keypoints=-1)[0]) >= k
