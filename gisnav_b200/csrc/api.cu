@@ -703,10 +703,54 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restric
     if (i < n) out[i] = __bfloat162float(in[i]);
 }
 
+// run the dense stack (and optionally K2 + K3 into slots [0, n)) on a batch of n images: parity hook for the
+// persistent multi-tile / multi-image loops of the conv kernels
+extern "C" int gnb_dense_batch(gnb_ctx* ctx, const uint8_t* images, int n, int h, int w, int dense_desc, int with_keypoints) {
+    if (!ctx || !images || n < 1) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_image(ctx, h, w))) return rc;
+    if (n > ctx->cfg.max_batch) { GNB_SET_ERR(ctx, "batch %d exceeds max_batch %d", n, ctx->cfg.max_batch); return GNB_E_CAPACITY; }
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->cw.img, images, (size_t)n * h * w, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = gnb_conv_forward(ctx, n, h, w, dense_desc))) return rc;
+    if (with_keypoints) {
+        if ((rc = gnb_kp_select(ctx, ctx->cw.score, n, h, w, 0))) return rc;
+        if ((rc = gnb_describe(ctx, n, h, w, 0))) return rc;
+    }
+    GNB_SYNC(ctx);
+    return GNB_OK;
+}
+
+// keypoints + descriptors of keypoint slot `slot` (after gnb_dense_batch(with_keypoints) / gnb_pose_batch)
+extern "C" int gnb_slot_keypoints(gnb_ctx* ctx, int slot, float* out_xy, float* out_score, float* out_desc, int cap, int* n_out) {
+    if (!ctx || !n_out || slot < 0 || slot >= ctx->kp_slots) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int n = 0, rc;
+    if ((rc = read_count(ctx, ctx->kp_count + slot, &n))) return rc;
+    if (n < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); return GNB_E_CAPACITY; }
+    n = n < cap ? n : cap;
+    *n_out = n;
+    const size_t k = ctx->cfg.max_keypoints;
+    if (n > 0) {
+        if (out_xy) GNB_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->kp_xy + slot * k * 2, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_score) GNB_CUDA(ctx, cudaMemcpyAsync(out_score, ctx->kp_score + slot * k, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_desc) GNB_CUDA(ctx, cudaMemcpyAsync(out_desc, ctx->desc_f32 + slot * k * 256, sizeof(float) * 256 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        GNB_SYNC(ctx);
+    }
+    return GNB_OK;
+}
+
+extern "C" int gnb_layer_activation_at(gnb_ctx* ctx, const char* layer, int image_index, float* out, size_t out_floats);
 extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out, size_t out_floats) {
+    return gnb_layer_activation_at(ctx, layer, 0, out, out_floats);
+}
+
+extern "C" int gnb_layer_activation_at(gnb_ctx* ctx, const char* layer, int image_index, float* out, size_t out_floats) {
     if (!ctx || !layer || !out) return GNB_E_INVALID;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     const ConvWorkspace& cw = ctx->cw;
+    if (image_index < 0 || image_index >= cw.n) { GNB_SET_ERR(ctx, "image index %d outside the last pass (%d images)", image_index, cw.n); return GNB_E_INVALID; }
+    const size_t ii = (size_t)image_index;
     struct { const char* name; const bf16* p; int div, c; } tbl[] = {
         {"conv1a", cw.a1a, 1, 64}, {"pool1", cw.p1, 2, 64},   {"conv2a", cw.a2a, 2, 64}, {"pool2", cw.p2, 4, 64},
         {"conv3a", cw.a3a, 4, 128}, {"pool3", cw.p3, 8, 128}, {"conv4a", cw.a4a, 8, 128}, {"conv4b", cw.a4b, 8, 128},
@@ -718,7 +762,7 @@ extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out,
             if (n != out_floats) { GNB_SET_ERR(ctx, "layer %s has %zu floats, caller passed %zu", layer, n, out_floats); return GNB_E_INVALID; }
             int rc;
             if ((rc = gnb_ensure_stage(ctx, n, 0))) return rc;
-            GNB_KERNEL(ctx, "bf16_to_f32_kernel", bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t.p, ctx->stage_a, n));
+            GNB_KERNEL(ctx, "bf16_to_f32_kernel", bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t.p + ii * n, ctx->stage_a, n));
             GNB_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage_a, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
             GNB_SYNC(ctx);
             return GNB_OK;
@@ -727,7 +771,15 @@ extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out,
     if (strcmp(layer, "semi") == 0) {
         const size_t n = (size_t)(cw.h / 8) * (cw.w / 8) * 65;
         if (n != out_floats) return GNB_E_INVALID;
-        GNB_CUDA(ctx, cudaMemcpyAsync(out, cw.semi, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        GNB_CUDA(ctx, cudaMemcpyAsync(out, cw.semi + ii * n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        GNB_SYNC(ctx);
+        return GNB_OK;
+    }
+    if (strcmp(layer, "score") == 0 || strcmp(layer, "dense") == 0) {
+        const bool sc = layer[0] == 's';
+        const size_t n = sc ? (size_t)cw.h * cw.w : (size_t)(cw.h / 8) * (cw.w / 8) * 256;
+        if (n != out_floats) { GNB_SET_ERR(ctx, "layer %s has %zu floats, caller passed %zu", layer, n, out_floats); return GNB_E_INVALID; }
+        GNB_CUDA(ctx, cudaMemcpyAsync(out, (sc ? cw.score : cw.dense) + ii * n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         GNB_SYNC(ctx);
         return GNB_OK;
     }

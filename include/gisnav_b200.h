@@ -196,6 +196,16 @@ int gnb_dense(gnb_ctx* ctx, const uint8_t* image, int h, int w, int stride, floa
 /* K1 per-layer taps: layer in {"conv1a","pool1","conv2a","pool2","conv3a","pool3","conv4a","conv4b",
  * "convPa","convDa"} after running gnb_dense; out f32 [hl,wl,c] (converted from bf16). */
 int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out, size_t out_floats);
+/* K1 on a batch of n images u8 [n,h,w] (host), n <= max_batch: the dense stack, optionally the dense
+ * descriptor map (dense_desc) and K2 + K3 into keypoint slots [0, n) (with_keypoints).  Parity hook for
+ * the persistent multi-tile, multi-image loops of the conv kernels at BASELINE.json's full sizes. */
+int gnb_dense_batch(gnb_ctx* ctx, const uint8_t* images, int n, int h, int w, int dense_desc, int with_keypoints);
+/* gnb_layer_activation for image `image_index` of the last pass; also accepts "score" (f32 [h,w]) and
+ * "dense" (f32 [h/8,w/8,256], only after a pass with dense_desc). */
+int gnb_layer_activation_at(gnb_ctx* ctx, const char* layer, int image_index, float* out, size_t out_floats);
+/* keypoints (x, y) f32 [n,2], scores f32 [n] and descriptors f32 [n,256] held in keypoint slot `slot`
+ * (slots [0, max_batch) = query frames / gnb_dense_batch images, [max_batch, 2 max_batch) = rasters). */
+int gnb_slot_keypoints(gnb_ctx* ctx, int slot, float* out_xy, float* out_score, float* out_desc, int cap, int* n_out);
 /* K2: NMS + threshold + border + top-K on a caller-supplied score map. */
 int gnb_select_keypoints(gnb_ctx* ctx, const float* score, int h, int w, float* out_xy, float* out_score,
                          int cap, int* n_out);

@@ -9,6 +9,12 @@ Numerics contract shared with the CUDA path ("bf16 operands, fp32 accumulate"): 
 its input activations and weights rounded to bfloat16 (round-to-nearest-even), accumulates in
 fp32, adds an fp32 bias and applies ReLU in fp32.  Head outputs (65 logits, 256-d raw descriptors)
 stay fp32.  ``quantize=False`` gives the plain fp32 network for reporting the bf16 deviation.
+
+``quantize="x3"`` is the contract of the library's fp32-faithful mode (``conv_precision = 1``): every
+conv operand is split into two bf16 terms, ``v = hi + lo`` with ``hi = bf16(v)``, ``lo = bf16(v - hi)``
+(16 significant bits), and the product keeps the three leading terms
+``a_hi w_hi + a_hi w_lo + a_lo w_hi`` accumulated in fp32 — what three tcgen05 MMAs into one TMEM
+accumulator compute.  Relative error per product ~2^-16 against 2^-8 for plain bf16 operands.
 """
 from __future__ import annotations
 
@@ -19,14 +25,28 @@ import torch
 import torch.nn.functional as F
 
 
-def _q(x: torch.Tensor, quantize: bool) -> torch.Tensor:
+def _q(x: torch.Tensor, quantize) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32) if quantize else x
+
+
+def split_hi_lo(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """v -> (hi, lo), both bf16-representable fp32 tensors with v ~= hi + lo to 2^-17 relative."""
+    hi = x.to(torch.bfloat16).to(torch.float32)
+    lo = (x - hi).to(torch.bfloat16).to(torch.float32)
+    return hi, lo
 
 
 def _conv(x, p, name, relu=True, quantize=True):
     w = torch.from_numpy(p[name + ".weight"])
     b = torch.from_numpy(p[name + ".bias"])
-    y = F.conv2d(_q(x, quantize), _q(w, quantize), b, padding=w.shape[-1] // 2)
+    pad = w.shape[-1] // 2
+    if quantize == "x3":
+        xh, xl = split_hi_lo(x)
+        wh, wl = split_hi_lo(w)
+        # the two small terms first, then the leading one and the bias (fp32 accumulation throughout)
+        y = (F.conv2d(xh, wl, None, padding=pad) + F.conv2d(xl, wh, None, padding=pad)) + F.conv2d(xh, wh, b, padding=pad)
+    else:
+        y = F.conv2d(_q(x, quantize), _q(w, quantize), b, padding=pad)
     return F.relu(y) if relu else y
 
 
