@@ -41,6 +41,7 @@ class GnbConfig(C.Structure):
         ("conv_impl", C.c_int32),
         ("match_impl", C.c_int32),
         ("tile_cache", C.c_int32),
+        ("precision", C.c_int32),
     ]
 
 

@@ -31,6 +31,7 @@ class Config:
     conv_impl: Optional[int] = None  # 0 tcgen05 (product), 1 SIMT validation kernel; None = library default
     match_impl: Optional[int] = None
     tile_cache: int = 32  # reference-raster feature cache entries
+    precision: int = 0  # 0 = bf16 operands (fast); 1 = split-bf16 x3 + fp32 heads/matcher (fp32-faithful)
 
     def __post_init__(self):
         if self.conv_impl is None or self.match_impl is None:

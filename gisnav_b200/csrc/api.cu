@@ -61,6 +61,14 @@ extern "C" int gnb_profile_read(gnb_ctx* ctx, char* names, float* total_ms, int6
     return GNB_OK;
 }
 
+cudaError_t gnb_func_smem_impl(gnb_ctx* ctx, const void* func, int bytes) {
+    for (int i = 0; i < ctx->n_attr_funcs; ++i)
+        if (ctx->attr_funcs[i] == func) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && ctx->n_attr_funcs < (int)(sizeof(ctx->attr_funcs) / sizeof(ctx->attr_funcs[0]))) ctx->attr_funcs[ctx->n_attr_funcs++] = func;
+    return e;
+}
+
 extern "C" int gnb_default_config(gnb_config* cfg) {
     if (!cfg) return GNB_E_INVALID;
     memset(cfg, 0, sizeof(*cfg));
@@ -80,6 +88,7 @@ extern "C" int gnb_default_config(gnb_config* cfg) {
     cfg->conv_impl = 0;   // tcgen05 implicit GEMM
     cfg->match_impl = 0;  // tcgen05 descriptor GEMM
     cfg->tile_cache = 32;
+    cfg->precision = 0;   // bf16 operands (fast mode); 1 = split-bf16 operands, fp32-faithful
     return GNB_OK;
 }
 
@@ -124,16 +133,17 @@ static int alloc_workspace(gnb_ctx* ctx) {
     rc |= dalloc(ctx, &cw.img_a, n * px);
     rc |= dalloc(ctx, &cw.img_b, n * px);
     cw.img = cw.img_a;
-    rc |= dalloc(ctx, &cw.a1a, n * px * 64);
-    rc |= dalloc(ctx, &cw.p1, n * px / 4 * 64);
-    rc |= dalloc(ctx, &cw.a2a, n * px / 4 * 64);
-    rc |= dalloc(ctx, &cw.p2, n * px / 16 * 64);
-    rc |= dalloc(ctx, &cw.a3a, n * px / 16 * 128);
-    rc |= dalloc(ctx, &cw.p3, n * px / 64 * 128);
-    rc |= dalloc(ctx, &cw.a4a, n * px / 64 * 128);
-    rc |= dalloc(ctx, &cw.a4b, n * px / 64 * 128);
-    rc |= dalloc(ctx, &cw.apa, n * px / 64 * 256);
-    rc |= dalloc(ctx, &cw.ada, n * px / 64 * 256);
+    const size_t pf = c.precision == 1 ? 2 : 1;   // fp32-faithful mode: every activation is a (hi, lo) pair of bf16
+    rc |= dalloc(ctx, &cw.a1a, n * px * 64 * pf);
+    rc |= dalloc(ctx, &cw.p1, n * px / 4 * 64 * pf);
+    rc |= dalloc(ctx, &cw.a2a, n * px / 4 * 64 * pf);
+    rc |= dalloc(ctx, &cw.p2, n * px / 16 * 64 * pf);
+    rc |= dalloc(ctx, &cw.a3a, n * px / 16 * 128 * pf);
+    rc |= dalloc(ctx, &cw.p3, n * px / 64 * 128 * pf);
+    rc |= dalloc(ctx, &cw.a4a, n * px / 64 * 128 * pf);
+    rc |= dalloc(ctx, &cw.a4b, n * px / 64 * 128 * pf);
+    rc |= dalloc(ctx, &cw.apa, n * px / 64 * 256 * pf);
+    rc |= dalloc(ctx, &cw.ada, n * px / 64 * 256 * pf);
     rc |= dalloc(ctx, &cw.semi, n * px / 64 * 65);
     rc |= dalloc(ctx, &cw.score, n * px);
     rc |= dalloc(ctx, &cw.dense, n * px / 64 * 256);
@@ -171,7 +181,14 @@ static int alloc_workspace(gnb_ctx* ctx) {
     rc |= dalloc(ctx, &ctx->c_kp_count, cc);
     rc |= dalloc(ctx, &ctx->c_mproj, cc * k * 256);
     rc |= dalloc(ctx, &ctx->c_mlogit, cc * k);
+    if (c.precision == 1) {
+        rc |= dalloc(ctx, &ctx->mproj_f32, slots * k * 256);
+        rc |= dalloc(ctx, &ctx->c_mproj_f32, cc * k * 256);
+        rc |= dalloc(ctx, &ctx->head_tmp, n * k * 4 + n * k * 4 * 256);
+    }
     if (rc) return GNB_E_CUDA;
+    if (c.precision == 1) GNB_CUDA(ctx, cudaMemset(ctx->mproj_f32, 0, slots * k * 256 * sizeof(float)));
+    GNB_CUDA(ctx, cudaMemset(ctx->desc_f32, 0, slots * k * 256 * sizeof(float)));
     ctx->cache_ids = new long long[cc];
     ctx->cache_lru = new unsigned long long[cc];
     for (size_t i = 0; i < cc; ++i) { ctx->cache_ids[i] = -1; ctx->cache_lru[i] = 0; }
@@ -196,7 +213,8 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->desc_f32, ctx->mproj, ctx->mlogit, ctx->row_lse, ctx->best_val, ctx->best_idx, ctx->match_idx,
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
-                    ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf};
+                    ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf,
+                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->head_tmp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
@@ -236,6 +254,10 @@ extern "C" int gnb_create(const gnb_config* cfg, const void* weights, size_t nby
     if (cfg->max_keypoints < 16 || cfg->max_keypoints > GNB_MAX_KP || cfg->max_batch < 1 || cfg->ransac_iters < 1 ||
         cfg->max_image_h % 8 || cfg->max_image_w % 8 || cfg->max_image_h < 16 || cfg->max_image_w < 16) {
         snprintf(g_create_err, sizeof(g_create_err), "invalid config (K in [16,%d], sides multiple of 8)", GNB_MAX_KP);
+        return GNB_E_INVALID;
+    }
+    if (cfg->precision != 0 && cfg->precision != 1) {
+        snprintf(g_create_err, sizeof(g_create_err), "invalid config: precision must be 0 (bf16) or 1 (fp32-faithful)");
         return GNB_E_INVALID;
     }
     gnb_ctx* ctx = new (std::nothrow) gnb_ctx();
@@ -283,7 +305,7 @@ extern "C" int gnb_create(const gnb_config* cfg, const void* weights, size_t nby
     const float* head = fl + (expect_floats - (256 * 256 + 256 + 256 + 1));
     if ((rc = gnb_match_init(ctx, head, head + 256 * 256, head + 256 * 256 + 256, head[256 * 256 + 512]))) return fail(rc);
     if ((rc = alloc_workspace(ctx))) return fail(rc);
-    if (cfg->conv_impl == 0 && (rc = gnb_conv_tc_init(ctx))) return fail(rc);
+    if ((cfg->conv_impl == 0 || cfg->precision == 1) && (rc = gnb_conv_tc_init(ctx))) return fail(rc);
     if (cfg->match_impl == 0 && (rc = gnb_match_tc_init(ctx))) return fail(rc);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { GNB_SET_ERR(ctx, "init sync failed"); return fail(GNB_E_CUDA); }
     *out = ctx;
@@ -584,7 +606,10 @@ static void cache_copy(gnb_ctx* ctx, int entry, int slot, bool to_cache) {
         cp(ctx->c_desc + (size_t)entry * k * 256, ctx->desc_f32 + (size_t)slot * k * 256, k * 256 * sizeof(float));
         return;
     }
-    cp(ctx->c_mproj + (size_t)entry * k * 256, ctx->mproj + (size_t)slot * k * 256, k * 256 * sizeof(bf16));
+    if (ctx->cfg.precision == 1)
+        cp(ctx->c_mproj_f32 + (size_t)entry * k * 256, ctx->mproj_f32 + (size_t)slot * k * 256, k * 256 * sizeof(float));
+    else
+        cp(ctx->c_mproj + (size_t)entry * k * 256, ctx->mproj + (size_t)slot * k * 256, k * 256 * sizeof(bf16));
     cp(ctx->c_mlogit + (size_t)entry * k, ctx->mlogit + (size_t)slot * k, k * sizeof(float));
 }
 
@@ -698,6 +723,8 @@ extern "C" int gnb_dense(gnb_ctx* ctx, const uint8_t* image, int h, int w, int s
     return GNB_OK;
 }
 
+int gnb_split_to_f32(gnb_ctx* ctx, const bf16* in, float* out, size_t pixels, int c);   // conv_x3.cu
+
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __bfloat162float(in[i]);
@@ -762,6 +789,12 @@ extern "C" int gnb_layer_activation_at(gnb_ctx* ctx, const char* layer, int imag
             if (n != out_floats) { GNB_SET_ERR(ctx, "layer %s has %zu floats, caller passed %zu", layer, n, out_floats); return GNB_E_INVALID; }
             int rc;
             if ((rc = gnb_ensure_stage(ctx, n, 0))) return rc;
+            if (ctx->cfg.precision == 1) {
+                if ((rc = gnb_split_to_f32(ctx, t.p + ii * 2 * n, ctx->stage_a, n / t.c, t.c))) return rc;
+                GNB_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage_a, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+                GNB_SYNC(ctx);
+                return GNB_OK;
+            }
             GNB_KERNEL(ctx, "bf16_to_f32_kernel", bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(t.p + ii * n, ctx->stage_a, n));
             GNB_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage_a, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
             GNB_SYNC(ctx);

@@ -20,6 +20,9 @@ struct ConvLayer {
     int cin, cout, ks, cout_pad;
     bf16* w;      // device, [ks*ks][cout_pad][cin]  (K-major per tap: tcgen05 B operand / SIMT)
     float* bias;  // device, [cout_pad]
+    // fp32-faithful mode (cfg.precision = 1) only:
+    bf16* w_x3;   // device, [ks*ks][cout_pad][2 cin]: per output row the hi terms of its cin weights, then the lo terms
+    float* w_f32; // device, [ks*ks][cout_pad][cin] fp32 (conv1a and the two 1x1 heads run on the CUDA cores in fp32)
 };
 
 // Per-image-slot activation pointers for one batched pass of the conv stack (all NHWC).
@@ -110,6 +113,15 @@ struct gnb_ctx {
     size_t warp_bytes;
     void* lg_state;                 // LgState* (lightglue.cu): transformer layers in front of the head, NULL = head only
     void* tc_state;                 // TcState* (tc_common.cuh): tensor maps bound to this context's buffers
+    int* tc_err_host;               // host-mapped word written by a timed-out tcgen05 pipeline wait (per context, portable)
+    int* tc_err_dev;
+    const void* attr_funcs[128];    // kernels whose dynamic shared-memory limit has been raised on THIS context's device
+    int n_attr_funcs;
+    float* match_w_f32;             // fp32-faithful mode: matcher head weights [256 out][256 in] / [256] in fp32
+    float* match_mw_f32;
+    float* mproj_f32;               // [slots][K][256] fp32 projected descriptors (fp32-faithful mode)
+    float* c_mproj_f32;             // [cache_cap][K][256] their cached copies
+    float* head_tmp;                // fp32-faithful mode: [n][cells][65] logits / gathered convDb rows
     // profiling
     int prof_on;
     void* prof;  // ProfState*
@@ -156,6 +168,12 @@ void gnb_prof_end(gnb_ctx* ctx);
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember per context (= per device) which
+// kernels have it raised, so two contexts on two GPUs of one process both get it (api.cu).
+cudaError_t gnb_func_smem_impl(gnb_ctx* ctx, const void* func, int bytes);
+template <typename F>
+static inline cudaError_t gnb_func_smem(gnb_ctx* ctx, F* func, int bytes) { return gnb_func_smem_impl(ctx, (const void*)func, bytes); }
 
 // ---- stage functions implemented across the .cu files (all enqueue on ctx->stream) -----------
 int gnb_conv_init(gnb_ctx* ctx, const float* blob_floats);  // repack weights

@@ -17,6 +17,11 @@ const CUtensorMap_st* gnb_conv_tc_wmap(gnb_ctx* ctx, int lid);
 int gnb_score_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* apa, const float* bias, int n, int hc, int wc, float* score);
 int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out_p1);
 int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0);
+// conv_x3.cu (fp32-faithful mode)
+int gnb_conv1a_x3(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out);
+int gnb_gemm256_f32(gnb_ctx* ctx, int amode, const void* a, const int* row_idx, int m_rows, const float* wgt, const float* bias, int n_cols,
+                    float scale, float* c, int ldc, const char* name);
+int gnb_describe_x3(gnb_ctx* ctx, int n, int h, int w, int slot0);
 
 // ------------------------------------------------------------------------------------------------
 // host-side bf16 rounding (round to nearest even), identical to torch's .to(bfloat16)
@@ -59,6 +64,29 @@ int gnb_conv_init(gnb_ctx* ctx, const float* blob) {
         GNB_CUDA(ctx, cudaMalloc(&L.bias, bp.size() * sizeof(float)));
         GNB_CUDA(ctx, cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         GNB_CUDA(ctx, cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (ctx->cfg.precision == 1) {
+            // fp32-faithful mode: w = hi + lo as two bf16 terms per weight ([tap][cout_pad][hi: cin | lo: cin]) for the
+            // tcgen05 layers, and the plain fp32 weights for the CUDA-core layers (conv1a, convPb, convDb)
+            std::vector<uint16_t> wx((size_t)taps * L.cout_pad * 2 * s.cin, 0);
+            std::vector<float> wf((size_t)taps * L.cout_pad * s.cin, 0.f);
+            for (int co = 0; co < s.cout; ++co)
+                for (int ci = 0; ci < s.cin; ++ci)
+                    for (int t = 0; t < taps; ++t) {
+                        const float v = w[((size_t)co * s.cin + ci) * taps + t];
+                        const uint16_t hb = f32_to_bf16_bits(v);
+                        uint32_t hu = (uint32_t)hb << 16;
+                        float hf;
+                        memcpy(&hf, &hu, 4);
+                        const size_t row = ((size_t)t * L.cout_pad + co) * 2 * s.cin;
+                        wx[row + ci] = hb;
+                        wx[row + s.cin + ci] = f32_to_bf16_bits(v - hf);
+                        wf[((size_t)t * L.cout_pad + co) * s.cin + ci] = v;
+                    }
+            GNB_CUDA(ctx, cudaMalloc(&L.w_x3, wx.size() * sizeof(uint16_t)));
+            GNB_CUDA(ctx, cudaMalloc(&L.w_f32, wf.size() * sizeof(float)));
+            GNB_CUDA(ctx, cudaMemcpy(L.w_x3, wx.data(), wx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            GNB_CUDA(ctx, cudaMemcpy(L.w_f32, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
     }
     return GNB_OK;
 }
@@ -67,7 +95,9 @@ void gnb_conv_free(gnb_ctx* ctx) {
     for (int l = 0; l < GNB_NUM_LAYERS; ++l) {
         if (ctx->layers[l].w) cudaFree(ctx->layers[l].w);
         if (ctx->layers[l].bias) cudaFree(ctx->layers[l].bias);
-        ctx->layers[l].w = nullptr; ctx->layers[l].bias = nullptr;
+        if (ctx->layers[l].w_x3) cudaFree(ctx->layers[l].w_x3);
+        if (ctx->layers[l].w_f32) cudaFree(ctx->layers[l].w_f32);
+        ctx->layers[l].w = nullptr; ctx->layers[l].bias = nullptr; ctx->layers[l].w_x3 = nullptr; ctx->layers[l].w_f32 = nullptr;
     }
 }
 
@@ -213,11 +243,7 @@ static int launch_conv_simt(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, in
                             float* out_f, int relu, int pool) {
     constexpr int R = KS / 2;
     size_t smem = (((8 + 2 * R) * (16 + 2 * R) * (CIN + 2) * 2 + 15) / 16) * 16 + (size_t)KS * KS * 16 * CIN * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_simt_kernel<CIN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    GNB_CUDA(ctx, gnb_func_smem(ctx, conv_simt_kernel<CIN, KS>, (int)smem));
     dim3 grid(ceil_div(w, 16), ceil_div(h, 8), n);
     GNB_KERNEL(ctx, "conv_simt_kernel", conv_simt_kernel<CIN, KS><<<grid, 128, smem, ctx->stream>>>(in, L.w, L.bias, h, w, L.cout, L.cout_pad, out_bf, out_f, relu, pool));
     return GNB_OK;
@@ -226,7 +252,7 @@ static int launch_conv_simt(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, in
 static int conv_layer(gnb_ctx* ctx, int lid, const bf16* in, int n, int h, int w, bf16* out_bf, float* out_f,
                       int relu, int pool) {
     const ConvLayer& L = ctx->layers[lid];
-    if (ctx->cfg.conv_impl == 0) {
+    if (ctx->cfg.conv_impl == 0 || ctx->cfg.precision == 1) {
         int rc = gnb_conv_tc_layer(ctx, L, in, n, h, w, out_bf, out_f, relu, pool);
         if (rc != GNB_E_INVALID) return rc;
         GNB_SET_ERR(ctx, "tcgen05 conv does not support layer %d (cin %d cout %d ks %d)", lid, L.cin, L.cout, L.ks);
@@ -290,6 +316,27 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
     }
     cw.n = n; cw.h = h; cw.w = w;
     int rc;
+    if (ctx->cfg.precision == 1) {
+        // fp32-faithful mode: conv1a fp32 (CUDA cores) -> split-bf16 tcgen05 stack -> fp32 heads
+        if ((rc = gnb_conv1a_x3(ctx, cw.img, n, h, w, cw.a1a))) return rc;
+        if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
+        if ((rc = conv_layer(ctx, L2A, cw.p1, n, h / 2, w / 2, cw.a2a, nullptr, 1, 0))) return rc;
+        if ((rc = conv_layer(ctx, L2B, cw.a2a, n, h / 2, w / 2, cw.p2, nullptr, 1, 1))) return rc;
+        if ((rc = conv_layer(ctx, L3A, cw.p2, n, h / 4, w / 4, cw.a3a, nullptr, 1, 0))) return rc;
+        if ((rc = conv_layer(ctx, L3B, cw.a3a, n, h / 4, w / 4, cw.p3, nullptr, 1, 1))) return rc;
+        if ((rc = conv_layer(ctx, L4A, cw.p3, n, h / 8, w / 8, cw.a4a, nullptr, 1, 0))) return rc;
+        if ((rc = conv_layer(ctx, L4B, cw.a4a, n, h / 8, w / 8, cw.a4b, nullptr, 1, 0))) return rc;
+        if ((rc = conv_layer(ctx, LPA, cw.a4b, n, h / 8, w / 8, cw.apa, nullptr, 1, 0))) return rc;
+        const int cells = n * (h / 8) * (w / 8);
+        if ((rc = gnb_gemm256_f32(ctx, 1, cw.apa, nullptr, cells, ctx->layers[LPB].w_f32, ctx->layers[LPB].bias, 65, 1.0f, cw.semi, 65, "score_head_f32"))) return rc;
+        GNB_KERNEL(ctx, "softmax_d2s_kernel", softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score));
+        if ((rc = conv_layer(ctx, LDA, cw.a4b, n, h / 8, w / 8, cw.ada, nullptr, 1, 0))) return rc;
+        if (dense_desc) {
+            if ((rc = gnb_gemm256_f32(ctx, 1, cw.ada, nullptr, cells, ctx->layers[LDB].w_f32, ctx->layers[LDB].bias, 256, 1.0f, cw.dense, 256, "desc_dense_f32"))) return rc;
+            GNB_KERNEL(ctx, "l2norm256_kernel", l2norm256_kernel<<<ceil_div(cells * 32, 256), 256, 0, ctx->stream>>>(cw.dense, cells));
+        }
+        return GNB_OK;
+    }
     static const int no_fuse = getenv("GNB_NO_CONV1_FUSION") ? atoi(getenv("GNB_NO_CONV1_FUSION")) : 0;
     const bool fused1 = ctx->cfg.conv_impl == 0 && !no_fuse && (w % 16) == 0;  // TMA on the u8 image needs a 16-byte row pitch
     if (!fused1 || dense_desc) {
@@ -327,6 +374,7 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
 }
 
 int gnb_describe(gnb_ctx* ctx, int n, int h, int w, int slot0) {
+    if (ctx->cfg.precision == 1) return gnb_describe_x3(ctx, n, h, w, slot0);
     if (ctx->cfg.conv_impl == 0)
         return gnb_desc_head_tc(ctx, gnb_conv_tc_wmap(ctx, LDB), ctx->cw.ada, ctx->layers[LDB].bias, n, h, w, slot0);
     return gnb_kp_sample(ctx, ctx->cw.dense, n, h, w, slot0);

@@ -178,7 +178,14 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const __grid_constant__ CU
 // stage and the output channels are split into `n_slices` slices of NPAD channels: a CTA keeps the
 // weights of ONE slice resident for the whole layer (blockIdx.x % n_slices) and loops over tiles,
 // so the only streamed operand is the 22.5 KB halo box (L2 traffic per tile = n_slices x KCH x 22.5 KB).
-template <int NPAD, int KCH, int STAGES>
+//
+// X3 = the fp32-faithful mode (cfg.precision = 1, oracle/superpoint_ref.py quantize="x3"): activations and weights
+// travel as TWO bf16 terms per value, v = hi + lo, stored as channel blocks [hi: C | lo: C] of one NHWC tensor, so
+// the KCH = 2 C / 64 chunks of a pixel are the hi chunks followed by the lo chunks.  The product keeps
+// a_hi w_hi + a_hi w_lo + a_lo w_hi: a hi chunk is multiplied with the hi AND the lo weight block of the same
+// channels, a lo chunk with the hi block only — three MMAs into the same fp32 TMEM accumulator per (tap, k-step).
+// The epilogue splits the fp32 result again (hi = bf16(v), lo = bf16(v - hi)); pooling is done on the fp32 values.
+template <int NPAD, int KCH, int STAGES, bool X3 = false>
 __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_in,
                                                               const __grid_constant__ CUtensorMap tmap_w,
                                                               const float* __restrict__ bias, int h, int w, int n_img, int cout,
@@ -268,13 +275,23 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
                 tc::tc_fence_after();
                 const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
                 if (tc::elect_one()) {
+                    // X3: hi chunk -> weight blocks {hi, lo} of the same channels; lo chunk -> weight block hi
+                    constexpr int KH = KCH / 2;
+                    const int wc0 = X3 ? (c < KH ? c : c - KH) : c;
+                    const int n_terms = (X3 && c < KH) ? 2 : 1;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
+                    for (int term = 0; term < (X3 ? 2 : 1); ++term) {
+                        if (term < n_terms) {
+                            const int wc = wc0 + term * KH;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
-                            const uint64_t db = db0 + (uint64_t)(((t * KCH + c) * W_TAP_BYTES + k * 32) >> 4);
-                            tc::umma_bf16(d_tmem, da, db, idesc, (c | t | k) ? 1u : 0u);
+                            for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
+                                    const uint64_t db = db0 + (uint64_t)(((t * KCH + wc) * W_TAP_BYTES + k * 32) >> 4);
+                                    tc::umma_bf16(d_tmem, da, db, idesc, (c | term | t | k) ? 1u : 0u);
+                                }
+                            }
                         }
                     }
                     tc::umma_commit(&a_empty[s]);
@@ -286,6 +303,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int yl = 4 * q + (lane >> 3), xl = lane & 7;
+        const int opitch = X3 ? 2 * cout : cout;     // output channels per pixel (X3: hi block then lo block)
         int i = 0;
         for (int tile = tile0; tile < total; tile += tstride, ++i) {
             const int as = i & 1;
@@ -309,6 +327,19 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
                 uint32_t v[32];
                 tc::tmem_ld32(taddr + c0, v);
                 tc::tmem_ld_wait();
+                if constexpr (X3) {
+                    uint32_t phi[16], plo[16];
+                    tc::epilogue_split32(v, &s_bias[c0], relu, pool, phi, plo);
+                    if (writer) {
+                        uint4* oh = reinterpret_cast<uint4*>(out_bf + pix * opitch + ch0 + c0);
+                        uint4* ol = reinterpret_cast<uint4*>(out_bf + pix * opitch + cout + ch0 + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            oh[g] = make_uint4(phi[4 * g], phi[4 * g + 1], phi[4 * g + 2], phi[4 * g + 3]);
+                            ol[g] = make_uint4(plo[4 * g], plo[4 * g + 1], plo[4 * g + 2], plo[4 * g + 3]);
+                        }
+                    }
+                } else {
                 uint32_t packed[16];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -356,6 +387,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
 #pragma unroll
                     for (int g = 0; g < 4; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
                 }
+                }   // !X3
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -371,15 +403,11 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
     }
 }
 
-template <int NPAD, int KCH, int STAGES, bool TSTORE = false>
+template <int NPAD, int KCH, int STAGES, bool TSTORE = false, bool X3 = false>
 static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
                                bf16* out_bf, int relu, int pool, const char* name) {
     constexpr int smem = 1024 + 9 * KCH * NPAD * 128 + STAGES * H2_HALO_STRIDE + 256 + NPAD * 4 + (TSTORE ? 1024 + 16384 : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_kernel<NPAD, KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    GNB_CUDA(ctx, gnb_func_smem(ctx, conv_tc_halo_kernel<NPAD, KCH, STAGES, X3>, smem));
     const int n_slices = L.cout_pad / NPAD;
     const int total = ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n;
     int per_slice = ctx->sm_count / n_slices;
@@ -395,7 +423,7 @@ static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUten
         int rc = gnb_make_tmap_bf16(ctx, &tout, out_bf, 4, od, os, ob);
         if (rc) return rc;
     }
-    GNB_KERNEL(ctx, name, conv_tc_halo_kernel<NPAD, KCH, STAGES><<<grid, 256, smem, ctx->stream>>>(
+    GNB_KERNEL(ctx, name, conv_tc_halo_kernel<NPAD, KCH, STAGES, X3><<<grid, 256, smem, ctx->stream>>>(
         tin, tw, L.bias, h, w, n, L.cout, n_slices, out_bf, relu, pool, gnb_tc_err_dev(ctx), tout, tstore));
     return GNB_OK;
 }
@@ -412,13 +440,14 @@ static int launch_conv_tc_halo(gnb_ctx* ctx, const CUtensorMap& tin, const CUten
 //   completion with a remote mbarrier arrive), and its tcgen05.commit is multicast to the barriers of both CTAs.
 //   both: TMA producer for their own tile / weight half, epilogue for their own accumulator; the peer's epilogue
 //   warps release the accumulator stage on the leader's barrier.
-#define HP_N 128            // output channels per pair-slice
-#define HP_NH 64            // weight rows per CTA
-template <int KCH, int STAGES>
+// NP = output channels per pair-slice (128; 64 in the fp32-faithful X3 mode, whose 2x as many resident weight blocks
+// leave room for 32 weight rows per CTA), X3 as in conv_tc_halo_kernel.
+template <int KCH, int STAGES, int NP = 128, bool X3 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, int h, int w, int n_img, int cout, int n_slices,
                          bf16* __restrict__ out_bf, int relu, int pool, int* err) {
+    constexpr int HP_N = NP, HP_NH = NP / 2;
     constexpr int W_TAP_BYTES = HP_NH * 128;
     constexpr int W_BYTES = 9 * KCH * W_TAP_BYTES;
     constexpr int TMEM_COLS = 2 * HP_N;
@@ -522,13 +551,22 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
                 tc::tc_fence_after();
                 const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
                 if (tc::elect_one()) {
+                    constexpr int KH = KCH / 2;
+                    const int wc0 = X3 ? (c < KH ? c : c - KH) : c;
+                    const int n_terms = (X3 && c < KH) ? 2 : 1;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
+                    for (int term = 0; term < (X3 ? 2 : 1); ++term) {
+                        if (term < n_terms) {
+                            const int wc = wc0 + term * KH;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
-                            const uint64_t db = db0 + (uint64_t)(((t * KCH + c) * W_TAP_BYTES + k * 32) >> 4);
-                            tc::umma_bf16_pair(d_tmem, da, db, idesc, (c | t | k) ? 1u : 0u);
+                            for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
+                                    const uint64_t db = db0 + (uint64_t)(((t * KCH + wc) * W_TAP_BYTES + k * 32) >> 4);
+                                    tc::umma_bf16_pair(d_tmem, da, db, idesc, (c | term | t | k) ? 1u : 0u);
+                                }
+                            }
                         }
                     }
                     tc::umma_commit_pair(&a_empty[s]);
@@ -542,6 +580,7 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
         const int yl = 4 * q + (lane >> 3), xl = lane & 7;
         const uint32_t leader_te[2] = {tc::map_to_cta(&t_empty[0], 0), tc::map_to_cta(&t_empty[1], 0)};
         uint8_t* stg = reinterpret_cast<uint8_t*>(s_bias + HP_N) + (warp - 4) * 2048;
+        const int opitch = X3 ? 2 * cout : cout;
         int i = 0;
         for (int tp = tp0; tp < tile_pairs; tp += tpstride, ++i) {
             const int as = i & 1;
@@ -566,6 +605,19 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
                 uint32_t v[32];
                 tc::tmem_ld32(taddr + c0, v);
                 tc::tmem_ld_wait();
+                if constexpr (X3) {
+                    uint32_t phi[16], plo[16];
+                    tc::epilogue_split32(v, &s_bias[c0], relu, pool, phi, plo);
+                    if (writer) {
+                        uint4* oh = reinterpret_cast<uint4*>(out_bf + pix * opitch + ch0 + c0);
+                        uint4* ol = reinterpret_cast<uint4*>(out_bf + pix * opitch + cout + ch0 + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            oh[g] = make_uint4(phi[4 * g], phi[4 * g + 1], phi[4 * g + 2], phi[4 * g + 3]);
+                            ol[g] = make_uint4(plo[4 * g], plo[4 * g + 1], plo[4 * g + 2], plo[4 * g + 3]);
+                        }
+                    }
+                } else {
                 uint32_t packed[16];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -612,6 +664,7 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
                     }
                     __syncwarp();
                 }
+                }   // !X3
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -627,22 +680,18 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
     }
 }
 
-template <int KCH, int STAGES>
+template <int KCH, int STAGES, int NP = 128, bool X3 = false>
 static int launch_conv_tc_halo_pair(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
                                     bf16* out_bf, int relu, int pool, const char* name) {
-    constexpr int smem = 1024 + 9 * KCH * HP_NH * 128 + STAGES * H2_HALO_STRIDE + 256 + HP_N * 4 + 4 * 2048;   // + write-out staging
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_pair_kernel<KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    const int n_slices = L.cout_pad / HP_N;
+    constexpr int smem = 1024 + 9 * KCH * (NP / 2) * 128 + STAGES * H2_HALO_STRIDE + 256 + NP * 4 + (X3 ? 0 : 4 * 2048);   // + write-out staging
+    GNB_CUDA(ctx, gnb_func_smem(ctx, conv_tc_halo_pair_kernel<KCH, STAGES, NP, X3>, smem));
+    const int n_slices = L.cout_pad / NP;
     const int tile_pairs = (ceil_div(w, H2_TW) * ceil_div(h, H2_TH) * n + 1) / 2;
     int per_slice = (ctx->sm_count / 2) / n_slices;
     if (per_slice > tile_pairs) per_slice = tile_pairs;
     if (per_slice < 1) per_slice = 1;
     const int grid = 2 * per_slice * n_slices;
-    GNB_KERNEL(ctx, name, conv_tc_halo_pair_kernel<KCH, STAGES><<<grid, 256, smem, ctx->stream>>>(
+    GNB_KERNEL(ctx, name, conv_tc_halo_pair_kernel<KCH, STAGES, NP, X3><<<grid, 256, smem, ctx->stream>>>(
         tin, tw, L.bias, h, w, n, L.cout, n_slices, out_bf, relu, pool, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
@@ -944,11 +993,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_kernel(const __grid
 
 int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out_p1) {
     if (((h | w) & 1) || (w % 16)) return GNB_E_INVALID;   // TMA: row pitch must be a multiple of 16 bytes
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM));
-        attr_set = true;
-    }
+    GNB_CUDA(ctx, gnb_func_smem(ctx, conv1_fused_kernel, F1_SMEM));
     gnb_encode_tiled_fn fn = gnb_get_encode_tiled(ctx);
     if (!fn) return GNB_E_CUDA;
     CUtensorMap timg;
@@ -970,11 +1015,7 @@ template <int NPAD>
 static int launch_conv_tc(gnb_ctx* ctx, const CUtensorMap& tin, const CUtensorMap& tw, const ConvLayer& L, int n, int h, int w,
                           bf16* out_bf, float* out_f, int relu, int pool, const char* name) {
     constexpr int smem = CT_STAGES * (CT_A_BYTES + NPAD * 128) + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    GNB_CUDA(ctx, gnb_func_smem(ctx, conv_tc_kernel<NPAD>, smem));
     dim3 grid(ceil_div(w, CT_TW), ceil_div(h, CT_TH), n);
     GNB_KERNEL(ctx, name, conv_tc_kernel<NPAD><<<grid, 256, smem, ctx->stream>>>(
         tin, tw, L.bias, h, w, L.cin, L.ks, L.cout, out_bf, out_f, relu, pool, gnb_tc_err_dev(ctx)));
@@ -1004,6 +1045,15 @@ int gnb_conv_tc_init(gnb_ctx* ctx) {
             const uint32_t box128[3] = {64, 128, 1};
             if ((rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].w128, L.w, 3, dims, strides, box128))) return rc;
         }
+        if (ctx->cfg.precision == 1 && L.ks == 3) {
+            // split weights [tap][cout_pad][hi: cin | lo: cin]: chunk c of the inner dimension is a hi chunk for
+            // c < cin / 64 and the matching lo chunk after that
+            const uint64_t xd[3] = {(uint64_t)L.cin * 2, (uint64_t)L.cout_pad, (uint64_t)(L.ks * L.ks)};
+            const uint64_t xs[2] = {(uint64_t)L.cin * 4, (uint64_t)L.cout_pad * L.cin * 4};
+            const uint32_t xb64[3] = {64, 64, 1}, xb32[3] = {64, 32, 1};
+            if ((rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].x64, L.w_x3, 3, xd, xs, xb64))) return rc;
+            if ((rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].x32, L.w_x3, 3, xd, xs, xb32))) return rc;
+        }
         g_wmaps[l].valid = 1;
     }
     return GNB_OK;
@@ -1019,9 +1069,23 @@ int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, i
                                                  "conv_tc:4a", "conv_tc:4b", "conv_tc:Pa", "conv_tc:Pb", "conv_tc:Da", "conv_tc:Db"};
     static const int v1_only = getenv("GNB_CONV_TC_V1") ? atoi(getenv("GNB_CONV_TC_V1")) : 0;
     CUtensorMap tin;
+    int rc;
+    if (ctx->cfg.precision == 1) {
+        // fp32-faithful mode: split activations [n][h][w][hi: cin | lo: cin], three MMAs per product (X3 kernels)
+        if (L.ks != 3 || !out_bf || (L.cin != 64 && L.cin != 128) || (L.cout_pad % 64)) return GNB_E_INVALID;
+        const uint64_t xd[4] = {(uint64_t)L.cin * 2, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        const uint64_t xs[3] = {(uint64_t)L.cin * 4, (uint64_t)w * L.cin * 4, (uint64_t)h * w * L.cin * 4};
+        const uint32_t hbox[4] = {64, H2_HW, H2_HH, 1};
+        if ((rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(in), 4, xd, xs, hbox))) return rc;
+        static const char* kNamesX3[GNB_NUM_LAYERS] = {"conv1a", "conv_x3:1b", "conv_x3:2a", "conv_x3:2b", "conv_x3:3a", "conv_x3:3b",
+                                                       "conv_x3:4a", "conv_x3:4b", "conv_x3:Pa", "conv_x3:Pb", "conv_x3:Da", "conv_x3:Db"};
+        if (L.cin == 64)    // single CTAs, 64-channel output slices, hi + lo weights of a slice resident (144 KB)
+            return launch_conv_tc_halo<64, 2, 3, false, true>(ctx, tin, g_wmaps[lid].x64, L, n, h, w, out_bf, relu, pool, kNamesX3[lid]);
+        // Cin = 128: CTA pairs, M = 256 x N = 64, each CTA keeps 32 rows of the hi + lo weights of all four chunks (144 KB)
+        return launch_conv_tc_halo_pair<4, 3, 64, true>(ctx, tin, g_wmaps[lid].x32, L, n, h, w, out_bf, relu, pool, kNamesX3[lid]);
+    }
     const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)L.cin * 2, (uint64_t)w * L.cin * 2, (uint64_t)h * w * L.cin * 2};
-    int rc;
     if (!v1_only && L.ks == 3 && out_bf && (L.cin == 64 || L.cin == 128) && (L.cout_pad % 64) == 0) {
         const uint32_t hbox[4] = {64, H2_HW, H2_HH, 1};
         if ((rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(in), 4, dims, strides, hbox))) return rc;
@@ -1030,7 +1094,7 @@ int gnb_conv_tc_layer(gnb_ctx* ctx, const ConvLayer& L, const bf16* in, int n, i
         if (L.cin == 64 && L.cout_pad == 128)
             return launch_conv_tc_halo<128, 1, 2, true>(ctx, tin, g_wmaps[lid].w128, L, n, h, w, out_bf, relu, pool, kNames[lid]);
         static const int no_pair = getenv("GNB_CONV_NO_PAIR") ? atoi(getenv("GNB_CONV_NO_PAIR")) : 0;
-        if (L.cin == 128 && !no_pair && (L.cout_pad % HP_N) == 0)   // CTA pairs: M = 256, N = 128 MMAs, half of the weight rows per SM
+        if (L.cin == 128 && !no_pair && (L.cout_pad % 128) == 0)   // CTA pairs: M = 256, N = 128 MMAs, half of the weight rows per SM
             return launch_conv_tc_halo_pair<2, 3>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);
         if (L.cin == 128)  // 128 -> 128 / 256: slices of 64 output channels, weights of a slice resident (144 KB)
             return launch_conv_tc_halo<64, 2, 3>(ctx, tin, g_wmaps[lid].w64, L, n, h, w, out_bf, relu, pool, kNames[lid]);

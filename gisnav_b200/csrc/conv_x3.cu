@@ -1,0 +1,286 @@
+// conv_x3.cu — the CUDA-core pieces of the fp32-faithful mode (cfg.precision = 1; contract in
+// oracle/superpoint_ref.py, quantize = "x3"; reference tensors are fp32 end to end,
+// ros/gisnav/gisnav/core/pose_node.py:254-287).
+//
+// In this mode every activation travels as two bf16 terms, v = hi + lo (16 significant bits), stored NHWC as
+// channel blocks [hi: C | lo: C]; the 3x3 layers with Cin >= 64 run on tcgen05 with three MMAs per product
+// (conv_tc.cu, X3 kernels).  What is left runs here in plain fp32 on the CUDA cores because it is < 1 % of the FLOPs:
+//   conv1a        (Cin = 1: nine FMAs per output, write-bound)          u8 image -> [hi|lo] x 64 channels
+//   convPb/convDb (1x1 heads, K = 256) as ONE generic SIMT GEMM         rows = cells (dense) or gathered cells (on demand)
+//   descriptor combine (per-cell L2 norm, bilinear, L2 norm)            oracle/sample_ref.py
+#include "common.cuh"
+
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------
+// conv1a, fp32: same tiling as conv1a_kernel (conv.cu).  Output pixel = 128 bf16: hi[64] then lo[64].
+#define X1_TH 8
+#define X1_TW 32
+__global__ void __launch_bounds__(256) conv1a_x3_kernel(const uint8_t* __restrict__ img, const float* __restrict__ wt,
+                                                        const float* __restrict__ bias, int h, int w, bf16* __restrict__ out) {
+    __shared__ float patch[X1_TH + 2][X1_TW + 2 + 2];
+    const int b = blockIdx.z, y0 = blockIdx.y * X1_TH, x0 = blockIdx.x * X1_TW;
+    const uint8_t* im = img + (size_t)b * h * w;
+    for (int i = threadIdx.x; i < (X1_TH + 2) * (X1_TW + 2); i += 256) {
+        const int ly = i / (X1_TW + 2), lx = i % (X1_TW + 2);
+        const int y = y0 + ly - 1, x = x0 + lx - 1;
+        float f = 0.f;
+        if (y >= 0 && y < h && x >= 0 && x < w) f = __fdiv_rn((float)im[(size_t)y * w + x], 255.0f);
+        patch[ly][lx] = f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = (lane & 7) * 8, sub = lane >> 3;
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wr[t][j] = wt[t * 64 + c0 + j];   // w_f32 [tap][cout_pad = 64][cin = 1]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) br[j] = bias[c0 + j];
+    __syncthreads();
+    const int ly = warp, y = y0 + ly;
+    if (y >= h) return;
+#pragma unroll 2
+    for (int it = 0; it < X1_TW / 4; ++it) {
+        const int lx = it * 4 + sub, x = x0 + lx;
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = patch[ly + t / 3][lx + t % 3];
+        __align__(16) __nv_bfloat162 rh[4], rl[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { a0 = fmaf(v[t], wr[t][j], a0); a1 = fmaf(v[t], wr[t][j + 1], a1); }
+            a0 = fmaxf(a0 + br[j], 0.f); a1 = fmaxf(a1 + br[j + 1], 0.f);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(a0, a1);
+            rh[j / 2] = hi;
+            rl[j / 2] = __floats2bfloat162_rn(__fsub_rn(a0, __low2float(hi)), __fsub_rn(a1, __high2float(hi)));
+        }
+        if (x < w) {
+            bf16* o = out + ((size_t)b * h * w + (size_t)y * w + x) * 128 + c0;
+            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(rh);
+            *reinterpret_cast<uint4*>(o + 64) = *reinterpret_cast<const uint4*>(rl);
+        }
+    }
+}
+
+int gnb_conv1a_x3(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out) {
+    dim3 grid(ceil_div(w, X1_TW), ceil_div(h, X1_TH), n);
+    GNB_KERNEL(ctx, "conv1a_x3_kernel", conv1a_x3_kernel<<<grid, 256, 0, ctx->stream>>>(img, ctx->layers[L1A].w_f32, ctx->layers[L1A].bias, h, w, out));
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic fp32 SIMT GEMM with K = 256:  C[m][n] = scale * (bias[n] + sum_k A[m][k] W[n][k]).
+//   AMODE 0: A rows are fp32 [256]            (matcher head projection of the descriptors)
+//   AMODE 1: A rows are split activations: 256 bf16 hi then 256 bf16 lo; a = float(hi) + float(lo)
+// row_idx (optional): source row of output row m (-1 = all-zero row, output row = scale * bias); NULL = identity.
+// CTA = 64 x 64 output tile, 256 threads, 4 x 4 micro-tile per thread, K in steps of 32 through shared memory.
+template <int AMODE>
+__global__ void __launch_bounds__(256) gemm256_f32_kernel(const void* __restrict__ a, const int* __restrict__ row_idx, int m_rows,
+                                                          const float* __restrict__ wgt, const float* __restrict__ bias, int n_cols,
+                                                          float scale, float* __restrict__ c, int ldc) {
+    __shared__ float As[32][64 + 4];   // [k][m]
+    __shared__ float Ws[32][64 + 4];   // [k][n]
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // loader mapping: thread -> (row r = tid / 4, 8 consecutive k = (tid % 4) * 8)
+    const int lr = tid >> 2, lk = (tid & 3) * 8;
+    int src = -1;
+    if (m0 + lr < m_rows) src = row_idx ? row_idx[m0 + lr] : m0 + lr;
+    const bool wrow_ok = n0 + lr < n_cols;
+    for (int k0 = 0; k0 < 256; k0 += 32) {
+        float av[8], wv[8];
+        if (src >= 0) {
+            if (AMODE == 0) {
+                const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a) + (size_t)src * 256 + k0 + lk);
+                const float4 u = __ldg(p), v = __ldg(p + 1);
+                av[0] = u.x; av[1] = u.y; av[2] = u.z; av[3] = u.w; av[4] = v.x; av[5] = v.y; av[6] = v.z; av[7] = v.w;
+            } else {
+                const bf16* row = static_cast<const bf16*>(a) + (size_t)src * 512 + k0 + lk;
+                const uint4 hi = __ldg(reinterpret_cast<const uint4*>(row)), lo = __ldg(reinterpret_cast<const uint4*>(row + 256));
+                const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    av[2 * j] = __fadd_rn(__uint_as_float(hw[j] << 16), __uint_as_float(lw[j] << 16));
+                    av[2 * j + 1] = __fadd_rn(__uint_as_float(hw[j] & 0xffff0000u), __uint_as_float(lw[j] & 0xffff0000u));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) av[j] = 0.f;
+        }
+        if (wrow_ok) {
+            const float4* p = reinterpret_cast<const float4*>(wgt + (size_t)(n0 + lr) * 256 + k0 + lk);
+            const float4 u = __ldg(p), v = __ldg(p + 1);
+            wv[0] = u.x; wv[1] = u.y; wv[2] = u.z; wv[3] = u.w; wv[4] = v.x; wv[5] = v.y; wv[6] = v.z; wv[7] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wv[j] = 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { As[lk + j][lr] = av[j]; Ws[lk + j][lr] = wv[j]; }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float4 x = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 y = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float xa[4] = {x.x, x.y, x.z, x.w}, yb[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], yb[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= m_rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < n_cols) c[(size_t)m * ldc + n] = __fmul_rn(__fadd_rn(acc[i][j], bias[n]), scale);
+        }
+    }
+}
+
+int gnb_gemm256_f32(gnb_ctx* ctx, int amode, const void* a, const int* row_idx, int m_rows, const float* wgt, const float* bias, int n_cols,
+                    float scale, float* c, int ldc, const char* name) {
+    if (m_rows <= 0) return GNB_OK;
+    dim3 grid(ceil_div(m_rows, 64), ceil_div(n_cols, 64));
+    if (amode == 0)
+        GNB_KERNEL(ctx, name, gemm256_f32_kernel<0><<<grid, 256, 0, ctx->stream>>>(a, row_idx, m_rows, wgt, bias, n_cols, scale, c, ldc));
+    else
+        GNB_KERNEL(ctx, name, gemm256_f32_kernel<1><<<grid, 256, 0, ctx->stream>>>(a, row_idx, m_rows, wgt, bias, n_cols, scale, c, ldc));
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// On-demand descriptor head, fp32: (1) which four coarse cells does each keypoint touch, (2) convDb at those
+// cells through gemm256_f32_kernel, (3) per-cell L2 norm, bilinear combine, L2 norm (oracle/sample_ref.py).
+__global__ void __launch_bounds__(256) desc_cells_kernel(const float* __restrict__ kp_xy, const int* __restrict__ kp_count, int slot0,
+                                                         int k_cap, int hc, int wc, int img_h, int img_w, int* __restrict__ row_idx) {
+    const int b = blockIdx.y, slot = slot0 + b;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (keypoint, corner)
+    if (i >= k_cap * 4) return;
+    const int kp = i >> 2, corner = i & 3;
+    int idx = -1;
+    if (kp < kp_count[slot]) {
+        const float x = kp_xy[((size_t)slot * k_cap + kp) * 2 + 0], y = kp_xy[((size_t)slot * k_cap + kp) * 2 + 1];
+        const float gx = __fdiv_rn(__fsub_rn(x, 3.5f), (float)img_w - 4.5f);
+        const float gy = __fdiv_rn(__fsub_rn(y, 3.5f), (float)img_h - 4.5f);
+        const int cx = (int)floorf(__fmul_rn(gx, (float)(wc - 1))) + (corner & 1);
+        const int cy = (int)floorf(__fmul_rn(gy, (float)(hc - 1))) + (corner >> 1);
+        if (cx >= 0 && cx < wc && cy >= 0 && cy < hc) idx = (b * hc + cy) * wc + cx;
+    }
+    row_idx[(size_t)b * k_cap * 4 + i] = idx;
+}
+
+// one warp per keypoint; lane l owns channels [8l, 8l + 8).  rows: [n][k_cap][4][256] raw convDb outputs (+ bias).
+__global__ void __launch_bounds__(256) desc_combine_kernel(const float* __restrict__ rows, const int* __restrict__ row_idx,
+                                                           const float* __restrict__ kp_xy, const int* __restrict__ kp_count, int slot0,
+                                                           int k_cap, int hc, int wc, int img_h, int img_w, float* __restrict__ desc) {
+    const int b = blockIdx.y, slot = slot0 + b;
+    const int kp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (kp >= kp_count[slot]) return;
+    const float x = kp_xy[((size_t)slot * k_cap + kp) * 2 + 0], y = kp_xy[((size_t)slot * k_cap + kp) * 2 + 1];
+    const float gx = __fdiv_rn(__fsub_rn(x, 3.5f), (float)img_w - 4.5f);
+    const float gy = __fdiv_rn(__fsub_rn(y, 3.5f), (float)img_h - 4.5f);
+    const float fx = __fmul_rn(gx, (float)(wc - 1)), fy = __fmul_rn(gy, (float)(hc - 1));
+    const float ax = __fsub_rn(fx, floorf(fx)), ay = __fsub_rn(fy, floorf(fy));
+    const float wq[4] = {__fmul_rn(1.f - ax, 1.f - ay), __fmul_rn(ax, 1.f - ay), __fmul_rn(1.f - ax, ay), __fmul_rn(ax, ay)};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    const size_t base = ((size_t)b * k_cap + kp) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (row_idx[base + c] < 0) continue;   // outside the map: zeros (grid_sample padding)
+        const float4* p = reinterpret_cast<const float4*>(rows + (base + c) * 256 + lane * 8);
+        const float4 a = p[0], d = p[1];
+        const float t[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(t[j], t[j], ss);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize of the cell's descriptor
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(v[j], __fmul_rn(__fmul_rn(t[j], inv), wq[c]));
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    float4* o = reinterpret_cast<float4*>(desc + ((size_t)slot * k_cap + kp) * 256 + lane * 8);
+    o[0] = make_float4(v[0] / nrm, v[1] / nrm, v[2] / nrm, v[3] / nrm);
+    o[1] = make_float4(v[4] / nrm, v[5] / nrm, v[6] / nrm, v[7] / nrm);
+}
+
+int gnb_describe_x3(gnb_ctx* ctx, int n, int h, int w, int slot0) {
+    const int k = ctx->cfg.max_keypoints, hc = h / 8, wc = w / 8;
+    int* row_idx = reinterpret_cast<int*>(ctx->head_tmp);                          // [n][k][4]
+    float* rows = ctx->head_tmp + (size_t)ctx->cfg.max_batch * k * 4;              // [n][k][4][256]
+    dim3 g1(ceil_div(k * 4, 256), n);
+    GNB_KERNEL(ctx, "desc_cells_kernel", desc_cells_kernel<<<g1, 256, 0, ctx->stream>>>(ctx->kp_xy, ctx->kp_count, slot0, k, hc, wc, h, w, row_idx));
+    int rc = gnb_gemm256_f32(ctx, 1, ctx->cw.ada, row_idx, n * k * 4, ctx->layers[LDB].w_f32, ctx->layers[LDB].bias, 256, 1.0f, rows, 256,
+                             "desc_head_f32");
+    if (rc) return rc;
+    dim3 g2(ceil_div(k * 32, 256), n);
+    GNB_KERNEL(ctx, "desc_combine_kernel", desc_combine_kernel<<<g2, 256, 0, ctx->stream>>>(rows, row_idx, ctx->kp_xy, ctx->kp_count, slot0, k, hc, wc, h, w,
+                                                                                       ctx->desc_f32));
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity hook: split activation [pixels][hi: c | lo: c] -> f32 [pixels][c]
+__global__ void split_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t pixels, int c) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels * c) return;
+    const size_t p = i / c;
+    const int ch = (int)(i - p * c);
+    out[i] = __fadd_rn(__bfloat162float(in[p * 2 * c + ch]), __bfloat162float(in[p * 2 * c + c + ch]));
+}
+
+int gnb_split_to_f32(gnb_ctx* ctx, const bf16* in, float* out, size_t pixels, int c) {
+    const size_t n = pixels * c;
+    GNB_KERNEL(ctx, "split_to_f32_kernel", split_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, pixels, c));
+    return GNB_OK;
+}
+
+// matchability logit in fp32: one warp per keypoint
+__global__ void __launch_bounds__(256) mlogit_f32_kernel(const float* __restrict__ desc, const int* __restrict__ kp_count, int slot0, int k_cap,
+                                                         const float* __restrict__ mw, float mb, float* __restrict__ mlogit) {
+    const int slot = slot0 + blockIdx.y;
+    const int kp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (kp >= kp_count[slot]) return;
+    const float* d = desc + ((size_t)slot * k_cap + kp) * 256;
+    float z = 0.f;
+    for (int i = lane; i < 256; i += 32) z = fmaf(d[i], mw[i], z);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) z += __shfl_xor_sync(0xffffffffu, z, s);
+    z += mb;
+    if (lane == 0) mlogit[(size_t)slot * k_cap + kp] = fminf(z, 0.f) - log1pf(expf(-fabsf(z)));
+}
+
+int gnb_project_f32(gnb_ctx* ctx, int slot0, int n_slots) {
+    const int k = ctx->cfg.max_keypoints;
+    // rows beyond a slot's keypoint count are projected too (finite garbage-free: the buffers are zero-initialised
+    // and only rows < count are ever read by the matcher)
+    int rc = gnb_gemm256_f32(ctx, 0, ctx->desc_f32 + (size_t)slot0 * k * 256, nullptr, n_slots * k, ctx->match_w_f32, ctx->match_b, 256, 0.25f,
+                             ctx->mproj_f32 + (size_t)slot0 * k * 256, 256, "project_f32");
+    if (rc) return rc;
+    dim3 grid(ceil_div(k * 32, 256), n_slots);
+    GNB_KERNEL(ctx, "mlogit_f32_kernel", mlogit_f32_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->desc_f32, ctx->kp_count, slot0, k, ctx->match_mw_f32,
+                                                                                   ctx->match_mb, ctx->mlogit));
+    return GNB_OK;
+}

@@ -162,11 +162,7 @@ int gnb_score_head_tc(gnb_ctx* ctx, const CUtensorMap* tmap_w, const bf16* apa, 
     const uint32_t box[4] = {64, 16, 8, 1};
     int rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(apa), 4, dims, strides, box);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(score_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM));
-        attr_set = true;
-    }
+    GNB_CUDA(ctx, gnb_func_smem(ctx, score_head_kernel, SH_SMEM));
     const int total = ceil_div(wc, 16) * ceil_div(hc, 8) * n;
     const int grid = total < ctx->sm_count ? total : ctx->sm_count;
     GNB_KERNEL(ctx, "score_head_tc", score_head_kernel<<<grid, 256, SH_SMEM, ctx->stream>>>(tin, *tmap_w, bias, hc, wc, n, score,
@@ -330,11 +326,7 @@ __global__ void __launch_bounds__(256, 1) desc_head_kernel(const __grid_constant
 }
 
 int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GNB_CUDA(ctx, cudaFuncSetAttribute(desc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DH_SMEM));
-        attr_set = true;
-    }
+    GNB_CUDA(ctx, gnb_func_smem(ctx, desc_head_kernel, DH_SMEM));
     const int k = ctx->cfg.max_keypoints;
     dim3 grid(ceil_div(k, 32), n);
     GNB_KERNEL(ctx, "desc_head_tc", desc_head_kernel<<<grid, 256, DH_SMEM, ctx->stream>>>(

@@ -410,21 +410,13 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
     GNB_CUDA(ctx, cudaMemsetAsync(ctx->cand_count + slot0, 0, sizeof(int) * n, ctx->stream));
     if (ctx->cfg.nms_radius == 4) {
         const size_t smem = (size_t)N4_REG * N4_PITCH * 2 * sizeof(float) + 3 * N4_REG * N4_WORDS * sizeof(unsigned);
-        static bool attr4 = false;
-        if (!attr4) {
-            GNB_CUDA(ctx, cudaFuncSetAttribute(nms_r4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr4 = true;
-        }
+        GNB_CUDA(ctx, gnb_func_smem(ctx, nms_r4_kernel, (int)smem));
         dim3 grid(ceil_div(w, N4_TILE), ceil_div(h, N4_TILE), n);
         GNB_KERNEL(ctx, "nms_r4_kernel", nms_r4_kernel<<<grid, N4_THREADS, smem, ctx->stream>>>(
             score, h, w, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count));
     } else {
         const size_t smem = (size_t)NMS_REG * NMS_REG * (4 * sizeof(float) + 2);
-        static bool attr_set = false;
-        if (!attr_set) {
-            GNB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
+        GNB_CUDA(ctx, gnb_func_smem(ctx, nms_kernel, (int)smem));
         dim3 grid(ceil_div(w, NMS_TILE), ceil_div(h, NMS_TILE), n);
         GNB_KERNEL(ctx, "nms_kernel", nms_kernel<<<grid, 256, smem, ctx->stream>>>(score, h, w, ctx->cfg.nms_radius, ctx->cfg.keypoint_threshold,
                                                      ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count));

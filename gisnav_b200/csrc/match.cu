@@ -41,6 +41,12 @@ int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const
     GNB_CUDA(ctx, cudaMemcpy(ctx->match_b, proj_b, 256 * 4, cudaMemcpyHostToDevice));
     GNB_CUDA(ctx, cudaMemcpy(ctx->match_mw, mw.data(), 256 * 2, cudaMemcpyHostToDevice));
     ctx->match_mb = m_b;
+    if (ctx->cfg.precision == 1) {   // fp32-faithful mode: the head runs in fp32 on the CUDA cores
+        GNB_CUDA(ctx, cudaMalloc(&ctx->match_w_f32, 256 * 256 * 4));
+        GNB_CUDA(ctx, cudaMalloc(&ctx->match_mw_f32, 256 * 4));
+        GNB_CUDA(ctx, cudaMemcpy(ctx->match_w_f32, proj_w, 256 * 256 * 4, cudaMemcpyHostToDevice));
+        GNB_CUDA(ctx, cudaMemcpy(ctx->match_mw_f32, m_w, 256 * 4, cudaMemcpyHostToDevice));
+    }
     return GNB_OK;
 }
 
@@ -49,6 +55,8 @@ void gnb_match_free(gnb_ctx* ctx) {
     if (ctx->match_b) cudaFree(ctx->match_b);
     if (ctx->match_mw) cudaFree(ctx->match_mw);
     if (ctx->match_wt) { cudaFree(ctx->match_wt); ctx->match_wt = nullptr; }
+    if (ctx->match_w_f32) { cudaFree(ctx->match_w_f32); ctx->match_w_f32 = nullptr; }
+    if (ctx->match_mw_f32) { cudaFree(ctx->match_mw_f32); ctx->match_mw_f32 = nullptr; }
     ctx->match_w = nullptr; ctx->match_b = nullptr; ctx->match_mw = nullptr;
 }
 
@@ -96,8 +104,10 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
 }
 
 int gnb_project_tc(gnb_ctx* ctx, int slot0, int n_slots);
+int gnb_project_f32(gnb_ctx* ctx, int slot0, int n_slots);   // conv_x3.cu
 
 int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots) {
+    if (ctx->cfg.precision == 1) return gnb_project_f32(ctx, slot0, n_slots);
     if (ctx->cfg.match_impl == 0) return gnb_project_tc(ctx, slot0, n_slots);
     const int k = ctx->cfg.max_keypoints;
     dim3 grid(ceil_div(k, 8), n_slots);
@@ -110,8 +120,12 @@ int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots) {
 // SIMT tile pass.  CTA = 64 rows of side R against all columns of side C, 64 columns at a time;
 // thread (ty,tx) owns a 4x4 micro-tile.  PASS 0: row log-sum-exp.  PASS 1: row argmax of the full
 // assignment score.
-template <int PASS>
-__global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ mproj, const float* __restrict__ mlogit,
+__device__ __forceinline__ float mt_load(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float mt_load(const float* p) { return *p; }
+
+// T = bf16 (validation of the tcgen05 kernels) or float (the fp32-faithful mode's matcher: cfg.precision = 1)
+template <int PASS, typename T>
+__global__ void __launch_bounds__(256) match_rows_simt(const T* __restrict__ mproj, const float* __restrict__ mlogit,
                                                        const int* __restrict__ kp_count, int k_cap, int slot_a0,
                                                        int stride_a, int slot_b0, int max_pairs, float* __restrict__ row_lse,
                                                        float* __restrict__ best_val, int* __restrict__ best_idx) {
@@ -127,11 +141,11 @@ __global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ 
     const int r0 = blockIdx.x * 64;
     if (r0 >= nr) return;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    const bf16* A = mproj + (size_t)slot_r * k_cap * 256;
-    const bf16* B = mproj + (size_t)slot_c * k_cap * 256;
+    const T* A = mproj + (size_t)slot_r * k_cap * 256;
+    const T* B = mproj + (size_t)slot_c * k_cap * 256;
     for (int i = tid; i < 64 * 256; i += 256) {
         const int r = i >> 8, k = i & 255;
-        As[k * 64 + r] = (r0 + r < nr) ? __bfloat162float(A[(size_t)(r0 + r) * 256 + k]) : 0.f;
+        As[k * 64 + r] = (r0 + r < nr) ? mt_load(&A[(size_t)(r0 + r) * 256 + k]) : 0.f;
     }
     float run_max[4], run_sum[4], bv[4], rl[4], la[4];
     int bi[4];
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(256) match_rows_simt(const bf16* __restrict__ 
         __syncthreads();
         for (int i = tid; i < 64 * 256; i += 256) {
             const int c = i >> 8, k = i & 255;
-            Bs[k * 64 + c] = (c0 + c < nc) ? __bfloat162float(B[(size_t)(c0 + c) * 256 + k]) : 0.f;
+            Bs[k * 64 + c] = (c0 + c < nc) ? mt_load(&B[(size_t)(c0 + c) * 256 + k]) : 0.f;
         }
         __syncthreads();
         float acc[4][4];
@@ -281,22 +295,25 @@ __global__ void __launch_bounds__(1024) mutual_kernel(const float* __restrict__ 
 int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a) {
     const int mp = ctx->cfg.max_batch;
     const int k = ctx->cfg.max_keypoints;
-    if (ctx->cfg.match_impl == 0) {
+    const size_t smem = 2 * 256 * 64 * sizeof(float);
+    dim3 grid(ceil_div(k, 64), pairs, 2);
+    if (ctx->cfg.precision == 1) {
+        GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<0, float>, (int)smem));
+        GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<1, float>, (int)smem));
+        GNB_KERNEL(ctx, "match_rows_f32<0>", match_rows_simt<0, float><<<grid, 256, smem, ctx->stream>>>(ctx->mproj_f32, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
+                                                             ctx->row_lse, ctx->best_val, ctx->best_idx));
+        GNB_KERNEL(ctx, "match_rows_f32<1>", match_rows_simt<1, float><<<grid, 256, smem, ctx->stream>>>(ctx->mproj_f32, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
+                                                             ctx->row_lse, ctx->best_val, ctx->best_idx));
+    } else if (ctx->cfg.match_impl == 0) {
         int rc;
         if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, stride_a, 0))) return rc;
         if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, stride_a, 1))) return rc;
     } else {
-        const size_t smem = 2 * 256 * 64 * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_simt<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_simt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
-        dim3 grid(ceil_div(k, 64), pairs, 2);
-        GNB_KERNEL(ctx, "match_rows_simt<0>", match_rows_simt<0><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
+        GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<0, bf16>, (int)smem));
+        GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<1, bf16>, (int)smem));
+        GNB_KERNEL(ctx, "match_rows_simt<0>", match_rows_simt<0, bf16><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
                                                              ctx->row_lse, ctx->best_val, ctx->best_idx));
-        GNB_KERNEL(ctx, "match_rows_simt<1>", match_rows_simt<1><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
+        GNB_KERNEL(ctx, "match_rows_simt<1>", match_rows_simt<1, bf16><<<grid, 256, smem, ctx->stream>>>(ctx->mproj, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
                                                              ctx->row_lse, ctx->best_val, ctx->best_idx));
     }
     GNB_KERNEL(ctx, "mutual_kernel", mutual_kernel<<<pairs, 1024, 0, ctx->stream>>>(ctx->best_val, ctx->best_idx, ctx->kp_count, ctx->kp_xy, k, slot_a0,

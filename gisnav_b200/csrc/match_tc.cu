@@ -25,9 +25,6 @@
 #define MT_THREADS (128 + 128 * MT_EPI_GROUPS)
 #define MT_SMEM_BYTES (1024 + MT_TILE_BYTES * (1 + MT_STAGES) + 256 + 2 * 2 * MT_BN * 4 + 3 * 128 * 4)
 
-static int* g_tc_err_host = nullptr;         // host-mapped error word written by timed-out waits
-static int* g_tc_err_dev = nullptr;
-
 gnb_encode_tiled_fn gnb_get_encode_tiled(gnb_ctx* ctx) {
     static gnb_encode_tiled_fn fn = nullptr;
     if (fn) return fn;
@@ -61,21 +58,23 @@ int gnb_make_tmap_bf16(gnb_ctx* ctx, CUtensorMap* out, void* base, int rank, con
 
 void gnb_tc_state_free(gnb_ctx* ctx) {
     if (ctx->tc_state) { delete static_cast<TcState*>(ctx->tc_state); ctx->tc_state = nullptr; }
+    if (ctx->tc_err_host) { cudaFreeHost(ctx->tc_err_host); ctx->tc_err_host = nullptr; ctx->tc_err_dev = nullptr; }
 }
 
 int* gnb_tc_err_dev(gnb_ctx* ctx) {
-    if (!g_tc_err_host) {
-        if (cudaHostAlloc((void**)&g_tc_err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
-        *g_tc_err_host = 0;
-        if (cudaHostGetDevicePointer((void**)&g_tc_err_dev, g_tc_err_host, 0) != cudaSuccess) return nullptr;
+    if (!ctx->tc_err_host) {
+        // portable: visible to every CUDA context of the process; one word per gnb_ctx so that two contexts
+        // (two GPUs, two host threads) never see each other's watchdog
+        if (cudaHostAlloc((void**)&ctx->tc_err_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        *ctx->tc_err_host = 0;
+        if (cudaHostGetDevicePointer((void**)&ctx->tc_err_dev, ctx->tc_err_host, 0) != cudaSuccess) return nullptr;
     }
-    (void)ctx;
-    return g_tc_err_dev;
+    return ctx->tc_err_dev;
 }
 int gnb_tc_err_check(gnb_ctx* ctx) {
-    if (g_tc_err_host && *g_tc_err_host) {
-        GNB_SET_ERR(ctx, "tcgen05 pipeline wait timed out (code %d)", *g_tc_err_host);
-        *g_tc_err_host = 0;
+    if (ctx->tc_err_host && *ctx->tc_err_host) {
+        GNB_SET_ERR(ctx, "tcgen05 pipeline wait timed out (code %d)", *ctx->tc_err_host);
+        *ctx->tc_err_host = 0;
         return GNB_E_CUDA;
     }
     return GNB_OK;
@@ -308,12 +307,12 @@ int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int 
     dim3 grid(ceil_div(k, MT_BM), pairs, pass == 2 ? 1 : 2);
     if (pass == 2)
         GNB_KERNEL(ctx, "match_rows_tc<2>", match_rows_tc<2><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, gnb_tc_err_dev(ctx)));
     else if (pass == 0)
         GNB_KERNEL(ctx, "match_rows_tc<0>", match_rows_tc<0><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, gnb_tc_err_dev(ctx)));
     else
         GNB_KERNEL(ctx, "match_rows_tc<1>", match_rows_tc<1><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, g_tc_err_dev));
+            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }

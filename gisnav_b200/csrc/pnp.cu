@@ -702,11 +702,7 @@ int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, in
     }
     {
         const size_t smem = (size_t)5 * k * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            GNB_CUDA(ctx, cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * GNB_MAX_KP * sizeof(float))));
-            attr_set = true;
-        }
+        GNB_CUDA(ctx, gnb_func_smem(ctx, score_kernel, (int)(5 * GNB_MAX_KP * sizeof(float))));
         dim3 grid(ceil_div(iters, 8 * 8), pairs);  // 8 warps per CTA, 8 hypotheses per warp
         GNB_KERNEL(ctx, "score_kernel", score_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->obj, ctx->mkp_qry, ctx->match_count, k, ctx->kmat, iters,
                                                        ctx->cfg.reproj_px, ctx->hyp, ctx->hyp_count));

@@ -177,6 +177,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return d;
 }
 
+// fp32-faithful mode (X3) epilogue for 32 accumulator columns of one pixel: v + bias, optional ReLU, optional 2x2
+// max-pool over the (lane ^ 1, lane ^ 8) neighbours ON THE FP32 VALUES, then the split v = hi + lo with
+// hi = bf16(v), lo = bf16(v - hi) (oracle/superpoint_ref.py split_hi_lo), each packed two channels per word.
+// Must be called by all 32 lanes of the warp when `pool` is set.
+__device__ __forceinline__ void epilogue_split32(const uint32_t v[32], const float* __restrict__ bias, int relu, int pool,
+                                                 uint32_t phi[16], uint32_t plo[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float a0 = __uint_as_float(v[2 * j]) + bias[2 * j], a1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+        if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+        if (pool) {
+            a0 = fmaxf(a0, __shfl_xor_sync(0xffffffffu, a0, 1)); a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, 1));
+            a0 = fmaxf(a0, __shfl_xor_sync(0xffffffffu, a0, 8)); a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, 8));
+        }
+        const uint32_t h = pack_bf16x2(a0, a1);
+        phi[j] = h;
+        plo[j] = pack_bf16x2(__fsub_rn(a0, __uint_as_float(h << 16)), __fsub_rn(a1, __uint_as_float(h & 0xffff0000u)));
+    }
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -253,7 +273,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }  // namespace tc
 
 // ---- per-context tensor maps (they embed device pointers of THIS context's buffers) -----------------
-struct TcLayerMaps { CUtensorMap w; CUtensorMap w64; CUtensorMap w128; int valid; };
+struct TcLayerMaps { CUtensorMap w; CUtensorMap w64; CUtensorMap w128; CUtensorMap x64; CUtensorMap x32; int valid; };   // x64/x32: split (hi|lo) weights, boxes of 64 / 32 rows
 struct TcState {
     TcLayerMaps layers[GNB_NUM_LAYERS];
     CUtensorMap match_map;   // mproj [slots][K][256]

@@ -69,6 +69,13 @@ typedef struct gnb_config {
     int32_t conv_impl;          /* 0 = tcgen05 implicit GEMM (product path); 1 = SIMT validation kernel */
     int32_t match_impl;         /* 0 = tcgen05 descriptor GEMM (product path); 1 = SIMT validation kernel */
     int32_t tile_cache;         /* reference-raster feature cache entries (>= max_batch; pose_node.py:226-241) */
+    int32_t precision;          /* arithmetic of the dense stack and the matcher head.
+                                   0 = fast: bf16 operands, fp32 accumulation (activations stored as bf16);
+                                   1 = fp32-faithful: every conv operand is split into two bf16 terms (v = hi + lo,
+                                       16 significant bits) and three tcgen05 MMAs (hi*hi + hi*lo + lo*hi) accumulate
+                                       into one fp32 TMEM accumulator; conv1a, the two 1x1 heads and the matcher head
+                                       run in plain fp32.  Reproduces the reference's fp32 tensors
+                                       (pose_node.py:254-287) to ~1e-5 relative; about 3x the tensor work. */
 } gnb_config;
 
 /* Fill cfg with the defaults listed above (K=1024, iters=2048, batch 8, 1088x1280 workspace). */

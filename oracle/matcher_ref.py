@@ -23,26 +23,28 @@ import torch
 import torch.nn.functional as F
 
 
-def _q(x: torch.Tensor) -> torch.Tensor:
-    return x.to(torch.bfloat16).to(torch.float32)
+def _q(x: torch.Tensor, quantize: bool = True) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32) if quantize else x
 
 
 @torch.no_grad()
-def project(desc: np.ndarray, params: Dict[str, np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
-    """desc f32 [n,256] -> (m bf16-valued f32 [n,256], matchability logit z f32 [n])."""
-    d = _q(torch.from_numpy(np.ascontiguousarray(desc, np.float32)))
-    w = _q(torch.from_numpy(params["match.proj.weight"]))
+def project(desc: np.ndarray, params: Dict[str, np.ndarray], quantize: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """desc f32 [n,256] -> (m f32 [n,256] (bf16-valued when ``quantize``), matchability logit z f32 [n]).
+    ``quantize=False`` is the plain fp32 head: the reference's tensors (pose_node.py:254-287) and the
+    library's fp32-faithful mode (``precision = 1``)."""
+    d = _q(torch.from_numpy(np.ascontiguousarray(desc, np.float32)), quantize)
+    w = _q(torch.from_numpy(params["match.proj.weight"]), quantize)
     b = torch.from_numpy(params["match.proj.bias"])
     m = (d @ w.t() + b) * np.float32(1.0 / desc.shape[1] ** 0.25)
-    wm = _q(torch.from_numpy(params["match.m.weight"]))
+    wm = _q(torch.from_numpy(params["match.m.weight"]), quantize)
     z = d @ wm + torch.from_numpy(params["match.m.bias"])[0]
-    return _q(m).numpy(), z.numpy()
+    return _q(m, quantize).numpy(), z.numpy()
 
 
 @torch.no_grad()
-def assignment_scores(desc_a, desc_b, params) -> np.ndarray:
-    ma, za = project(desc_a, params)
-    mb, zb = project(desc_b, params)
+def assignment_scores(desc_a, desc_b, params, quantize: bool = True) -> np.ndarray:
+    ma, za = project(desc_a, params, quantize)
+    mb, zb = project(desc_b, params, quantize)
     s = torch.from_numpy(ma) @ torch.from_numpy(mb).t()
     sc = (F.log_softmax(s, 1) + F.log_softmax(s, 0)
           + F.logsigmoid(torch.from_numpy(za))[:, None] + F.logsigmoid(torch.from_numpy(zb))[None, :])
@@ -51,12 +53,12 @@ def assignment_scores(desc_a, desc_b, params) -> np.ndarray:
 
 @torch.no_grad()
 def match(desc_a: np.ndarray, desc_b: np.ndarray, params: Dict[str, np.ndarray],
-          threshold: float = 0.5) -> Tuple[np.ndarray, np.ndarray]:
+          threshold: float = 0.5, quantize: bool = True) -> Tuple[np.ndarray, np.ndarray]:
     """-> (scores f32 [k,1], idx int64 [k,2]) sorted by query index, like the reference call."""
     n, m = desc_a.shape[0], desc_b.shape[0]
     if n == 0 or m == 0:
         return np.zeros((0, 1), np.float32), np.zeros((0, 2), np.int64)
-    sc = assignment_scores(desc_a, desc_b, params)
+    sc = assignment_scores(desc_a, desc_b, params, quantize)
     m0 = sc.argmax(1)  # numpy argmax returns the first maximum
     m1 = sc.argmax(0)
     i = np.arange(n)

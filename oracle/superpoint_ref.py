@@ -14,7 +14,9 @@ stay fp32.  ``quantize=False`` gives the plain fp32 network for reporting the bf
 conv operand is split into two bf16 terms, ``v = hi + lo`` with ``hi = bf16(v)``, ``lo = bf16(v - hi)``
 (16 significant bits), and the product keeps the three leading terms
 ``a_hi w_hi + a_hi w_lo + a_lo w_hi`` accumulated in fp32 — what three tcgen05 MMAs into one TMEM
-accumulator compute.  Relative error per product ~2^-16 against 2^-8 for plain bf16 operands.
+accumulator compute.  Relative error per product ~2^-16 against 2^-8 for plain bf16 operands.  conv1a (Cin = 1)
+and the two 1x1 heads (convPb, convDb) are plain fp32 in that mode (CUDA cores); the heads read the activation as
+stored, ``hi + lo``.
 """
 from __future__ import annotations
 
@@ -40,7 +42,13 @@ def _conv(x, p, name, relu=True, quantize=True):
     w = torch.from_numpy(p[name + ".weight"])
     b = torch.from_numpy(p[name + ".bias"])
     pad = w.shape[-1] // 2
-    if quantize == "x3":
+    if quantize == "x3" and name in ("conv1a", "convPb", "convDb"):
+        # < 1 % of the FLOPs: plain fp32 on the CUDA cores.  The 1x1 heads read the stored (hi, lo) activation.
+        if name != "conv1a":
+            xh, xl = split_hi_lo(x)
+            x = xh + xl
+        y = F.conv2d(x, w, b, padding=pad)
+    elif quantize == "x3":
         xh, xl = split_hi_lo(x)
         wh, wl = split_hi_lo(w)
         # the two small terms first, then the leading one and the bias (fp32 accumulation throughout)

@@ -32,7 +32,7 @@ def test_default_config_and_struct_layout():
     assert lib.gnb_default_config(C.byref(c)) == 0
     assert (c.max_keypoints, c.nms_radius, c.border, c.min_matches) == (1024, 4, 4, 15)
     assert abs(c.match_threshold - 0.5) < 1e-9 and abs(c.keypoint_threshold - 0.005) < 1e-9 and c.reproj_px == 8.0
-    assert C.sizeof(_lib.GnbConfig) == 16 * 4
+    assert C.sizeof(_lib.GnbConfig) == 17 * 4
     assert C.sizeof(_lib.GnbPoseResult) == 6 * 4 + 22 * 8
     d = gisnav_b200.Config()
     assert d.max_keypoints == c.max_keypoints and d.ransac_iters == c.ransac_iters

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """CPU study (oracle only): how far are the bf16 and the split-bf16 ("x3") conv contracts from the plain
-fp32 network, end to end?  For N config-2 pairs: keypoint-set overlap, match-set overlap and camera-centre
+fp32 network (fp32 matcher head included), end to end?  "bf16" = bf16 conv operands + bf16 matcher GEMM (the fast
+mode), "x3" = split-bf16 convs + fp32 heads + fp32 matcher (precision = 1).  For N config-2 pairs: keypoint-set overlap, match-set overlap and camera-centre
 difference against the fp32 oracle.  Writes one JSON line; used to set the tolerances of the fp32-faithful
 mode.
 
@@ -18,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run_pair(pair, params, mode, k_cap, iters):
+def run_pair(pair, params, mode, k_cap, iters, match_quant=True):
     from oracle import matcher_ref, nms_ref, pnp_ref, sample_ref, superpoint_ref
 
     feats = []
@@ -26,7 +27,7 @@ def run_pair(pair, params, mode, k_cap, iters):
         s, d = superpoint_ref.forward_dense(img, params, quantize=mode)
         xy, _ = nms_ref.select_keypoints(s, max_keypoints=k_cap)
         feats.append((xy, sample_ref.sample_descriptors(d, xy, img.shape)))
-    _, idx = matcher_ref.match(feats[0][1], feats[1][1], params, 0.5)
+    _, idx = matcher_ref.match(feats[0][1], feats[1][1], params, 0.5, quantize=match_quant)
     out = {"kp": [set(map(tuple, f[0].astype(int).tolist())) for f in feats]}
     out["matches"] = {(tuple(feats[0][0][i].astype(int)), tuple(feats[1][0][j].astype(int))) for i, j in idx.tolist()}
     out["centre"] = None
@@ -58,10 +59,10 @@ def main():
     t0 = time.time()
     for s in range(args.first_seed, args.first_seed + args.pairs):
         pair = synth.make_pair(ground, s, tuple(args.hw), args.tile)
-        ref = run_pair(pair, params, False, args.keypoints, args.iters)
+        ref = run_pair(pair, params, False, args.keypoints, args.iters, match_quant=False)   # fp32 everywhere
         row = {"seed": s}
         for name, mode in (("bf16", True), ("x3", "x3")):
-            got = run_pair(pair, params, mode, args.keypoints, args.iters)
+            got = run_pair(pair, params, mode, args.keypoints, args.iters, match_quant=(mode is True))
             kp_diff = sum(len(a ^ b) // 2 for a, b in zip(ref["kp"], got["kp"]))
             m_common = len(ref["matches"] & got["matches"])
             d = None
