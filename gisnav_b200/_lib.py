@@ -93,6 +93,7 @@ SIGNATURES = {
     "gnb_dense_batch": (_I, [_VP, _VP, _I, _I, _I, _I, _I]),
     "gnb_layer_activation_at": (_I, [_VP, C.c_char_p, _I, _VP, C.c_size_t]),
     "gnb_slot_keypoints": (_I, [_VP, _I, _VP, _VP, _VP, _I, C.POINTER(_I)]),
+    "gnb_pair_matches": (_I, [_VP, _I, _VP, _I, C.POINTER(_I)]),
     "gnb_select_keypoints": (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_sample_descriptors": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _I, _VP]),
     "gnb_match_scores": (_I, [_VP, _VP, _I, _VP, _I, _VP]),

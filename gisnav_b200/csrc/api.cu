@@ -767,6 +767,21 @@ extern "C" int gnb_slot_keypoints(gnb_ctx* ctx, int slot, float* out_xy, float* 
     return GNB_OK;
 }
 
+// match index pairs (query keypoint, reference keypoint) of pair `pair` of the last batch / matcher call
+extern "C" int gnb_pair_matches(gnb_ctx* ctx, int pair, int32_t* out_idx, int cap, int* n_out) {
+    if (!ctx || !n_out || pair < 0 || pair >= ctx->cfg.max_batch) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int n = 0, rc;
+    if ((rc = read_count(ctx, ctx->match_count + pair, &n))) return rc;
+    n = n < cap ? n : cap;
+    *n_out = n;
+    if (n > 0 && out_idx) {
+        GNB_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->match_idx + (size_t)pair * ctx->cfg.max_keypoints * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        GNB_SYNC(ctx);
+    }
+    return GNB_OK;
+}
+
 extern "C" int gnb_layer_activation_at(gnb_ctx* ctx, const char* layer, int image_index, float* out, size_t out_floats);
 extern "C" int gnb_layer_activation(gnb_ctx* ctx, const char* layer, float* out, size_t out_floats) {
     return gnb_layer_activation_at(ctx, layer, 0, out, out_floats);
@@ -875,6 +890,7 @@ __global__ void score_matrix_kernel(const bf16* __restrict__ ma, const bf16* __r
 extern "C" int gnb_match_scores(gnb_ctx* ctx, const float* desc_a, int n_a, const float* desc_b, int n_b, float* out_scores) {
     if (!ctx || !desc_a || !desc_b || !out_scores || n_a < 1 || n_b < 1) return GNB_E_INVALID;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->cfg.precision == 1) { GNB_SET_ERR(ctx, "gnb_match_scores is a hook of the bf16 matcher (precision = 0)"); return GNB_E_INVALID; }
     int rc;
     if ((rc = load_descs(ctx, desc_a, n_a, desc_b, n_b, 0))) return rc;
     if ((rc = gnb_match_pairs(ctx, 1, 0, ctx->cfg.max_batch))) return rc;  // fills row_lse for both sides

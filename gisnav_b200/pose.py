@@ -164,6 +164,25 @@ class PoseEstimator:
         best = max(ok, key=lambda i: out[i].n_inliers) if ok else None
         return best, out, hits.value
 
+    # ---- inspection of the last batch (accuracy reporting: keypoint / match sets per pair) ---------------
+    def slot_keypoints(self, slot: int, with_descriptors: bool = False):
+        """Keypoints (x, y) f32 [n,2] (+ descriptors f32 [n,256]) held in keypoint slot ``slot`` after a batch call:
+        slots [0, max_batch) are the query frames, [max_batch, 2 max_batch) the rasters."""
+        k = self.ctx.config.max_keypoints
+        xy = np.empty((k, 2), np.float32)
+        desc = np.empty((k, 256), np.float32) if with_descriptors else None
+        n = C.c_int(0)
+        self.ctx.check(self.ctx._lib.gnb_slot_keypoints(self.ctx.handle, slot, ptr(xy), None, ptr(desc), k, C.byref(n)))
+        return (xy[: n.value], desc[: n.value]) if with_descriptors else xy[: n.value]
+
+    def pair_matches(self, pair: int) -> np.ndarray:
+        """Match index pairs int32 [n,2] (query keypoint, raster keypoint) of pair ``pair`` of the last batch call."""
+        k = self.ctx.config.max_keypoints
+        idx = np.empty((k, 2), np.int32)
+        n = C.c_int(0)
+        self.ctx.check(self.ctx._lib.gnb_pair_matches(self.ctx.handle, pair, ptr(idx), k, C.byref(n)))
+        return idx[: n.value]
+
     def estimate_from_message(self, query: np.ndarray, reference: np.ndarray, dem: Optional[np.ndarray], camera_info,
                               crs: str) -> Optional[PoseResult]:
         """Fields of an ``OrthoStereoImage`` message (ros/gisnav_msgs/msg/OrthoStereoImage.msg:14-18) as

@@ -213,6 +213,9 @@ int gnb_layer_activation_at(gnb_ctx* ctx, const char* layer, int image_index, fl
 /* keypoints (x, y) f32 [n,2], scores f32 [n] and descriptors f32 [n,256] held in keypoint slot `slot`
  * (slots [0, max_batch) = query frames / gnb_dense_batch images, [max_batch, 2 max_batch) = rasters). */
 int gnb_slot_keypoints(gnb_ctx* ctx, int slot, float* out_xy, float* out_score, float* out_desc, int cap, int* n_out);
+/* match index pairs int32 [n,2] (query keypoint, reference keypoint; rows sorted by column 0) of pair `pair` of
+ * the last gnb_pose_batch / gnb_pose_candidates / matcher call. */
+int gnb_pair_matches(gnb_ctx* ctx, int pair, int32_t* out_idx, int cap, int* n_out);
 /* K2: NMS + threshold + border + top-K on a caller-supplied score map. */
 int gnb_select_keypoints(gnb_ctx* ctx, const float* score, int h, int w, float* out_xy, float* out_score,
                          int cap, int* n_out);
