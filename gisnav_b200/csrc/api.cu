@@ -152,6 +152,9 @@ static int alloc_workspace(gnb_ctx* ctx) {
     ctx->kp_slots = (int)slots;
     rc |= dalloc(ctx, &ctx->cand_keys, slots * GNB_CAND_CAP);
     rc |= dalloc(ctx, &ctx->cand_count, slots);
+    rc |= dalloc(ctx, &ctx->nms_hist, slots * 2048);
+    rc |= dalloc(ctx, &ctx->nms_level, slots);
+    rc |= dalloc(ctx, &ctx->nms_flag, slots);
     rc |= dalloc(ctx, &ctx->kp_xy, slots * k * 2);
     rc |= dalloc(ctx, &ctx->kp_score, slots * k);
     rc |= dalloc(ctx, &ctx->kp_count, slots);
@@ -194,6 +197,7 @@ static int alloc_workspace(gnb_ctx* ctx) {
     for (size_t i = 0; i < cc; ++i) { ctx->cache_ids[i] = -1; ctx->cache_lru[i] = 0; }
     ctx->cache_clock = 0;
     GNB_CUDA(ctx, cudaMemset(ctx->kp_count, 0, slots * sizeof(int)));
+    GNB_CUDA(ctx, cudaMemset(ctx->nms_hist, 0, slots * 2048 * sizeof(unsigned)));
     GNB_CUDA(ctx, cudaMemset(ctx->mproj, 0, slots * k * 256 * sizeof(bf16)));
     GNB_CUDA(ctx, cudaMemset(ctx->kp_xy, 0, slots * k * 2 * sizeof(float)));
     GNB_CUDA(ctx, cudaMallocHost((void**)&ctx->out_host, n * sizeof(PairOut)));
@@ -214,7 +218,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
                     ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf,
-                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->head_tmp};
+                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->head_tmp, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);

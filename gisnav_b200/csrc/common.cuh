@@ -68,6 +68,9 @@ struct gnb_ctx {
     int kp_slots;
     unsigned long long* cand_keys;  // [slots][GNB_CAND_CAP]
     int* cand_count;                // [slots]
+    unsigned* nms_hist;             // [slots][2048] score-bit histogram of the sparse NMS (keypoints.cu)
+    unsigned* nms_level;            // [slots] per-image level L: only pixels with score bits >= L are processed
+    int* nms_flag;                  // [slots] 1 = redo this image from the plain threshold
     float* kp_xy;                   // [slots][K][2]
     float* kp_score;                // [slots][K]
     int* kp_count;                  // [slots]

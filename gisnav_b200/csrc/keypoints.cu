@@ -10,6 +10,9 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+
+static inline unsigned __float_as_uint_host(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 
 #define NMS_TILE 32
 #define NMS_HALO 20  // 5 pools x radius 4
@@ -318,6 +321,262 @@ __global__ void __launch_bounds__(N4_THREADS, 2) nms_r4_kernel(const float* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sparse, top-K-aware NMS (radius 4) — the product path.
+//
+// Lemma (tests/test_oracle_cpu.py::test_nms_survivors_above_a_level_depend_only_on_pixels_above_it): for any level T
+// the survivors of simple_nms with score > T are unchanged when every pixel <= T is replaced by 0 — a pixel can only
+// suppress pixels that are not larger than itself.  Only the K best survivors are kept, and with the shipped weights
+// < 1 % (K = 1024) to 3 % (K = 2048) of the pixels score above the K-th survivor.  So:
+//   1. nms_hist_kernel   histogram of the score bit patterns (every 4th row: the level only steers the work, never the
+//                        result) -> nms_level_kernel picks, per image, a level L with ~32 K pixels at or above it
+//                        (never below the keypoint threshold);
+//   2. nms_sparse_kernel per 64x64 tile + 20 px halo: scores below L enter shared memory as 0, the pixels at or above
+//                        L form a short list, and every stage of simple_nms (window max, suppression dilation, two
+//                        refinement rounds) touches only listed pixels: a 3x3 pre-check, then the full 9x9 window for
+//                        the few that pass.  Compare-only arithmetic on the same values => the same decisions;
+//   3. nms_check_kernel  an image with fewer than K survivors above its level (rare: flat score maps) is flagged, its
+//                        level drops to the plain threshold and a second launch of nms_sparse_kernel (whose CTAs exit
+//                        at once when nothing is flagged) redoes that image exactly.
+// Bit-identical to oracle/nms_ref.py by construction; tests/test_gpu_parity.py::test_k2_* and test_gpu_fullsize.py.
+#define NS_TILE 64
+#define NS_REG 104
+#define NS_PITCH 105
+#define NS_WORDS 4
+#define NS_THREADS 256
+#define NS_BUCKETS 2048          // score bits >> 19: sign + exponent + 4 mantissa bits of a float in [0, 2)
+#define NS_HIST_ROW_STEP 4
+
+__global__ void __launch_bounds__(256) nms_hist_kernel(const float* __restrict__ score, int h, int w, unsigned thr_bits, int slot0,
+                                                       unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[NS_BUCKETS];
+    for (int i = threadIdx.x; i < NS_BUCKETS; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const int b = blockIdx.z;
+    const float* sc = score + (size_t)b * h * w;
+    const int rows = (h + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP;
+    const int total = rows * w;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / w, x = i - r * w;
+        const unsigned bits = __float_as_uint(__ldg(&sc[(size_t)(r * NS_HIST_ROW_STEP) * w + x]));
+        const bool act = (int)bits > (int)thr_bits && bits < 0x40000000u;   // thr < score < 2
+        if (act) {
+            const unsigned bucket = bits >> 19;
+            const unsigned peers = __match_any_sync(__activemask(), bucket);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bucket], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    unsigned* out = hist + (size_t)(slot0 + b) * NS_BUCKETS;
+    for (int i = threadIdx.x; i < NS_BUCKETS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&out[i], sh[i]);
+}
+
+// one warp per image: highest bucket edge with >= target sampled pixels at or above it
+__global__ void __launch_bounds__(32) nms_level_kernel(unsigned* __restrict__ hist, int slot0, unsigned target_sampled, unsigned thr_bits,
+                                                       unsigned* __restrict__ level, int* __restrict__ flag) {
+    const int slot = slot0 + blockIdx.x, lane = threadIdx.x;
+    unsigned* hs = hist + (size_t)slot * NS_BUCKETS;
+    constexpr int PER = NS_BUCKETS / 32;
+    unsigned mine = 0;
+    for (int i = 0; i < PER; ++i) mine += hs[lane * PER + i];
+    // suffix sums over lanes (lane 31 holds the highest buckets)
+    unsigned above = 0;   // pixels in lanes strictly above this one
+    for (int l = 31; l >= 0; --l) {
+        const unsigned v = __shfl_sync(0xffffffffu, mine, l);
+        if (lane < l) above += v;
+    }
+    // the crossing lane: above < target <= above + mine
+    const bool crossing = above < target_sampled && above + mine >= target_sampled;
+    unsigned edge = 0;   // bucket index; 0 = no crossing (fewer pixels than the target above the threshold)
+    if (crossing) {
+        unsigned acc = above;
+        for (int i = PER - 1; i >= 0; --i) {
+            acc += hs[lane * PER + i];
+            if (acc >= target_sampled) { edge = (unsigned)(lane * PER + i); break; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) edge = max(edge, __shfl_xor_sync(0xffffffffu, edge, o));
+    if (lane == 0) {
+        const unsigned lo = thr_bits + 1u;                    // score > threshold  <=>  bits >= thr_bits + 1 (non-negative floats)
+        const unsigned lv = max(edge << 19, lo);
+        level[slot] = lv;
+        flag[slot] = 0;
+    }
+    for (int i = lane; i < NS_BUCKETS; i += 32) hs[i] = 0u;   // ready for the next pass
+}
+
+__global__ void nms_check_kernel(int n, int slot0, int k_cap, unsigned thr_bits, int* __restrict__ cand_count,
+                                 unsigned* __restrict__ level, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = slot0 + i;
+    if (cand_count[slot] < k_cap && level[slot] > thr_bits + 1u) {   // too few survivors above the level: redo from the threshold
+        level[slot] = thr_bits + 1u;
+        flag[slot] = 1;
+        cand_count[slot] = 0;
+    } else {
+        flag[slot] = 0;
+    }
+}
+
+__device__ __forceinline__ unsigned ns_getbit(const unsigned* m, int y, int x) { return (m[y * NS_WORDS + (x >> 5)] >> (x & 31)) & 1u; }
+
+// 9x9 dilation of bit mask `in` into `out` (rows of 4 words), `tmp` holds the horizontal pass
+__device__ __forceinline__ void ns_dilate(const unsigned* __restrict__ in, unsigned* __restrict__ tmp, unsigned* __restrict__ out) {
+    for (int y = threadIdx.x; y < NS_REG; y += NS_THREADS) {
+        unsigned r[4], a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = in[y * NS_WORDS + i];
+        auto shl = [](const unsigned x[4], int s, unsigned o[4]) {
+            o[0] = x[0] << s;
+#pragma unroll
+            for (int i = 1; i < 4; ++i) o[i] = (x[i] << s) | (x[i - 1] >> (32 - s));
+        };
+        shl(r, 1, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] |= r[i];
+        shl(a, 2, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] |= b[i];
+        shl(a, 4, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] |= b[i];
+        shl(r, 8, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] |= b[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tmp[y * NS_WORDS + i] = (a[i] >> 4) | (i < 3 ? (a[i + 1] << 28) : 0u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NS_REG * NS_WORDS; i += NS_THREADS) {
+        const int y = i / NS_WORDS, wdx = i % NS_WORDS;
+        const int lo = max(y - 4, 0), hi = min(y + 4, NS_REG - 1);
+        unsigned acc = 0;
+        for (int yy = lo; yy <= hi; ++yy) acc |= tmp[yy * NS_WORDS + wdx];
+        out[i] = acc;
+    }
+}
+
+// is listed pixel (ly, lx) with score s >= every (unsuppressed) pixel of its 9x9 window?  3x3 ring first.
+template <bool USE_SUP>
+__device__ __forceinline__ bool ns_window_max(const float* __restrict__ S, const unsigned* __restrict__ SUP, int ly, int lx, float s) {
+    const int y_lo = max(ly - 4, 0), y_hi = min(ly + 4, NS_REG - 1), x_lo = max(lx - 4, 0), x_hi = min(lx + 4, NS_REG - 1);
+    // 3x3 ring (always inside the region for the positions that matter: callers restrict ly, lx to [4, 100))
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dy == 0 && dx == 0) continue;
+            const int yy = ly + dy, xx = lx + dx;
+            if (S[yy * NS_PITCH + xx] > s && !(USE_SUP && ns_getbit(SUP, yy, xx))) return false;
+        }
+    for (int yy = y_lo; yy <= y_hi; ++yy) {
+        const float* row = S + yy * NS_PITCH;
+        for (int xx = x_lo; xx <= x_hi; ++xx)
+            if (row[xx] > s && !(USE_SUP && ns_getbit(SUP, yy, xx))) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(NS_THREADS) nms_sparse_kernel(const float* __restrict__ score, int h, int w, int n_img, float threshold, int border,
+                                                                int slot0, const unsigned* __restrict__ level, const int* __restrict__ flag,
+                                                                int only_flagged, unsigned long long* __restrict__ cand_keys,
+                                                                int* __restrict__ cand_count) {
+    extern __shared__ float sm[];
+    float* S = sm;                                                       // scores at or above the level, 0 elsewhere
+    unsigned* ACT = reinterpret_cast<unsigned*>(S + NS_REG * NS_PITCH);  // listed pixels
+    unsigned* MAXM = ACT + NS_REG * NS_WORDS;                            // max_mask
+    unsigned* SUP = MAXM + NS_REG * NS_WORDS;                            // supp_mask
+    unsigned* TMP = SUP + NS_REG * NS_WORDS;
+    unsigned short* list = reinterpret_cast<unsigned short*>(TMP + NS_REG * NS_WORDS);   // [NS_REG * NS_REG] (ly << 8 | lx)
+    __shared__ int n_act;
+    const int tiles_x = (w + NS_TILE - 1) / NS_TILE, tiles_y = (h + NS_TILE - 1) / NS_TILE;
+    const int tiles = tiles_x * tiles_y, items = tiles * n_img;
+    const int lane = threadIdx.x & 31;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / tiles, t = item - b * tiles;
+        const int slot = slot0 + b;
+        if (only_flagged && !flag[slot]) continue;
+        const unsigned lv = level[slot];
+        const int y0 = (t / tiles_x) * NS_TILE - 20, x0 = (t % tiles_x) * NS_TILE - 20;
+        const float* sc = score + (size_t)b * h * w;
+        __syncthreads();   // previous item's shared memory is no longer read
+        if (threadIdx.x == 0) n_act = 0;
+        for (int i = threadIdx.x; i < NS_REG * NS_WORDS; i += NS_THREADS) MAXM[i] = 0u;
+        __syncthreads();
+        // ---- load: one slot per (row, column < 128); a warp covers one mask word
+        for (int i = threadIdx.x; i < NS_REG * 128; i += NS_THREADS) {
+            const int ly = i >> 7, lx = i & 127;
+            const int y = y0 + ly, x = x0 + lx;
+            float v = 0.f;
+            bool act = false;
+            if (lx < NS_REG && y >= 0 && y < h && x >= 0 && x < w) {
+                v = __ldg(&sc[(size_t)y * w + x]);
+                act = (int)__float_as_uint(v) >= (int)lv;
+            }
+            if (lx < NS_REG) S[ly * NS_PITCH + lx] = act ? v : 0.f;
+            const unsigned ballot = __ballot_sync(0xffffffffu, act);
+            if (lane == 0) ACT[ly * NS_WORDS + (lx >> 5)] = ballot;
+            if (ballot) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&n_act, __popc(ballot));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (act) list[base + __popc(ballot & ((1u << lane) - 1))] = (unsigned short)((ly << 8) | lx);
+            }
+        }
+        __syncthreads();
+        const int n = n_act;
+        if (n == 0) continue;   // uniform: nothing at or above the level in this region
+        // ---- max_mask = (score == 9x9 max), needed on [4, 100)^2
+        for (int e = threadIdx.x; e < n; e += NS_THREADS) {
+            const int ly = list[e] >> 8, lx = list[e] & 255;
+            if (ly < 4 || ly >= NS_REG - 4 || lx < 4 || lx >= NS_REG - 4) continue;
+            if (ns_window_max<false>(S, nullptr, ly, lx, S[ly * NS_PITCH + lx])) atomicOr(&MAXM[ly * NS_WORDS + (lx >> 5)], 1u << (lx & 31));
+        }
+        __syncthreads();
+        // ---- two refinement rounds: supp = dilate(max); new maxima among the unsuppressed
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+            ns_dilate(MAXM, TMP, SUP);
+            __syncthreads();
+            const int lo = it == 0 ? 12 : 20, hi = NS_REG - lo;   // where this round's result is still needed / valid
+            for (int e = threadIdx.x; e < n; e += NS_THREADS) {
+                const int ly = list[e] >> 8, lx = list[e] & 255;
+                if (ly < lo || ly >= hi || lx < lo || lx >= hi) continue;
+                if (ns_getbit(SUP, ly, lx)) continue;   // suppressed (covers every pixel that is already a maximum)
+                if (ns_window_max<true>(S, SUP, ly, lx, S[ly * NS_PITCH + lx])) atomicOr(&MAXM[ly * NS_WORDS + (lx >> 5)], 1u << (lx & 31));
+            }
+            __syncthreads();
+        }
+        // ---- emit the survivors of the central tile
+        for (int e0 = 0; e0 < n; e0 += NS_THREADS) {
+            const int e = e0 + threadIdx.x;
+            bool keep = false;
+            float s = 0.f;
+            int y = 0, x = 0;
+            if (e < n) {
+                const int ly = list[e] >> 8, lx = list[e] & 255;
+                y = y0 + ly; x = x0 + lx;
+                if (ly >= 20 && ly < 20 + NS_TILE && lx >= 20 && lx < 20 + NS_TILE && ns_getbit(MAXM, ly, lx)) {
+                    s = S[ly * NS_PITCH + lx];
+                    keep = s > threshold && y >= border && y < h - border && x >= border && x < w - border;
+                }
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int leader = __ffs(ballot) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&cand_count[slot], __popc(ballot));
+                base = __shfl_sync(ballot, base, leader);
+                const int pos = base + __popc(ballot & ((1u << lane) - 1));
+                if (pos < GNB_CAND_CAP)
+                    cand_keys[(size_t)slot * GNB_CAND_CAP + pos] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(s)) << 32) | (unsigned)(y * w + x);
+            }
+        }
+    }
+}
+
 // One CTA per image: exact top-K of the candidate keys (radix select on the 64-bit key), then a
 // bitonic sort of the K selected keys in shared memory.
 __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __restrict__ cand_keys,
@@ -408,7 +667,27 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         return GNB_E_INVALID;
     }
     GNB_CUDA(ctx, cudaMemsetAsync(ctx->cand_count + slot0, 0, sizeof(int) * n, ctx->stream));
-    if (ctx->cfg.nms_radius == 4) {
+    static const int dense_nms = getenv("GNB_NMS_DENSE") ? atoi(getenv("GNB_NMS_DENSE")) : 0;
+    if (ctx->cfg.nms_radius == 4 && ctx->cfg.keypoint_threshold >= 0.f && !dense_nms) {
+        // sparse, top-K-aware path (see above)
+        const int k_cap = ctx->cfg.max_keypoints;
+        const unsigned thr_bits = __float_as_uint_host(ctx->cfg.keypoint_threshold);
+        const unsigned target = (unsigned)((32ll * k_cap + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP);
+        const int rows = ceil_div(h, NS_HIST_ROW_STEP);
+        dim3 hgrid(min(ceil_div(rows * w, 256 * 8), 64), 1, n);
+        GNB_KERNEL(ctx, "nms_hist_kernel", nms_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(score, h, w, thr_bits, slot0, ctx->nms_hist));
+        GNB_KERNEL(ctx, "nms_level_kernel", nms_level_kernel<<<n, 32, 0, ctx->stream>>>(ctx->nms_hist, slot0, target, thr_bits, ctx->nms_level, ctx->nms_flag));
+        const size_t smem = (size_t)NS_REG * NS_PITCH * sizeof(float) + 4 * NS_REG * NS_WORDS * sizeof(unsigned) + (size_t)NS_REG * NS_REG * sizeof(unsigned short);
+        GNB_CUDA(ctx, gnb_func_smem(ctx, nms_sparse_kernel, (int)smem));
+        const int items = ceil_div(w, NS_TILE) * ceil_div(h, NS_TILE) * n;
+        const int grid = min(items, ctx->sm_count * 3);
+        GNB_KERNEL(ctx, "nms_sparse_kernel", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
+            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 0, ctx->cand_keys, ctx->cand_count));
+        GNB_KERNEL(ctx, "nms_check_kernel", nms_check_kernel<<<ceil_div(n, 64), 64, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->cand_count,
+                                                                                              ctx->nms_level, ctx->nms_flag));
+        GNB_KERNEL(ctx, "nms_sparse_kernel(redo)", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
+            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 1, ctx->cand_keys, ctx->cand_count));
+    } else if (ctx->cfg.nms_radius == 4) {
         const size_t smem = (size_t)N4_REG * N4_PITCH * 2 * sizeof(float) + 3 * N4_REG * N4_WORDS * sizeof(unsigned);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_r4_kernel, (int)smem));
         dim3 grid(ceil_div(w, N4_TILE), ceil_div(h, N4_TILE), n);

@@ -75,7 +75,7 @@ def test_k1_dense_matches_oracle(rand_blob, rand_params, oracle, impl, hw):
 
 
 # ---- K2: NMS + threshold + border + top-K (bit-exact) -------------------------------------------------
-@pytest.mark.parametrize("case", ["oracle_score", "random", "plateaus", "sparse", "empty", "tiny"])
+@pytest.mark.parametrize("case", ["oracle_score", "random", "plateaus", "sparse", "empty", "tiny", "redo_from_threshold", "negative_and_large"])
 def test_k2_keypoint_selection_bit_exact(rand_blob, stages, oracle, case):
     rng = np.random.default_rng(5)
     k = 64
@@ -94,6 +94,21 @@ def test_k2_keypoint_selection_bit_exact(rand_blob, stages, oracle, case):
             score[y, x] = v
     elif case == "empty":
         score = np.full((64, 64), 0.001, np.float32)
+    elif case == "redo_from_threshold":
+        # the sparse NMS picks a level with ~32 K pixels above it: here those all sit on ONE smooth bump (a single
+        # survivor), so the image must be redone from the plain threshold to find the low isolated peaks
+        yy, xx = np.mgrid[0:256, 0:320].astype(np.float32)
+        score = (0.9 * np.exp(-((yy - 120) ** 2 + (xx - 160) ** 2) / (2 * 80.0 ** 2))).astype(np.float32)
+        score[score < 0.3] = 0.0
+        for _ in range(600):
+            y, x = int(rng.integers(0, 256)), int(rng.integers(0, 320))
+            if score[y, x] == 0:
+                score[y, x] = np.float32(0.006 + 0.1 * rng.random())
+        k = 300
+    elif case == "negative_and_large":
+        score = (rng.standard_normal((96, 160)) * 0.7).astype(np.float32)     # negative scores and scores >= 2
+        score[10, 20] = 3.5; score[50, 80] = 2.0; score[51, 81] = 2.0
+        k = 100
     else:
         score = rng.random((16, 24)).astype(np.float32)
     ctx = _ctx(rand_blob, conv_impl=1, match_impl=1, max_keypoints=k)
