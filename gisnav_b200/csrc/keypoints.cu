@@ -341,11 +341,11 @@ __global__ void __launch_bounds__(N4_THREADS, 2) nms_r4_kernel(const float* __re
 // Bit-identical to oracle/nms_ref.py by construction; tests/test_gpu_parity.py::test_k2_* and test_gpu_fullsize.py.
 #define NS_TILE 64
 #define NS_REG 104
-#define NS_PITCH 105
+#define NS_PITCH 105   // odd pitch: the window scans walk columns
 #define NS_WORDS 4
 #define NS_THREADS 256
 #define NS_BUCKETS 2048          // score bits >> 19: sign + exponent + 4 mantissa bits of a float in [0, 2)
-#define NS_HIST_ROW_STEP 4
+#define NS_HIST_ROW_STEP 8
 
 __global__ void __launch_bounds__(256) nms_hist_kernel(const float* __restrict__ score, int h, int w, unsigned thr_bits, int slot0,
                                                        unsigned* __restrict__ hist) {
@@ -356,14 +356,26 @@ __global__ void __launch_bounds__(256) nms_hist_kernel(const float* __restrict__
     const float* sc = score + (size_t)b * h * w;
     const int rows = (h + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP;
     const int total = rows * w;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int r = i / w, x = i - r * w;
-        const unsigned bits = __float_as_uint(__ldg(&sc[(size_t)(r * NS_HIST_ROW_STEP) * w + x]));
-        const bool act = (int)bits > (int)thr_bits && bits < 0x40000000u;   // thr < score < 2
-        if (act) {
-            const unsigned bucket = bits >> 19;
-            const unsigned peers = __match_any_sync(__activemask(), bucket);
-            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bucket], (unsigned)__popc(peers));
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+        unsigned bits[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {     // four independent loads in flight
+            const int i = i0 + u * stride;
+            bits[u] = 0u;
+            if (i < total) {
+                const int r = i / w, x = i - r * w;
+                bits[u] = __float_as_uint(__ldg(&sc[(size_t)(r * NS_HIST_ROW_STEP) * w + x]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool act = (int)bits[u] > (int)thr_bits && bits[u] < 0x40000000u;   // thr < score < 2
+            if (act) {
+                const unsigned bucket = bits[u] >> 19;
+                const unsigned peers = __match_any_sync(__activemask(), bucket);
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bucket], (unsigned)__popc(peers));
+            }
         }
     }
     __syncthreads();
@@ -406,172 +418,261 @@ __global__ void __launch_bounds__(32) nms_level_kernel(unsigned* __restrict__ hi
     for (int i = lane; i < NS_BUCKETS; i += 32) hs[i] = 0u;   // ready for the next pass
 }
 
-__global__ void nms_check_kernel(int n, int slot0, int k_cap, unsigned thr_bits, int* __restrict__ cand_count,
-                                 unsigned* __restrict__ level, int* __restrict__ flag) {
+// first_count[slot] = survivors of the first pass; the counters of the images about to be redone restart at 0
+__global__ void nms_redo_prepare(int n, int slot0, int k_cap, unsigned thr_bits, const unsigned* __restrict__ level, int* __restrict__ cand_count,
+                                 int* __restrict__ first_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int slot = slot0 + i;
-    if (cand_count[slot] < k_cap && level[slot] > thr_bits + 1u) {   // too few survivors above the level: redo from the threshold
-        level[slot] = thr_bits + 1u;
-        flag[slot] = 1;
-        cand_count[slot] = 0;
-    } else {
-        flag[slot] = 0;
-    }
+    const int c = cand_count[slot];
+    first_count[slot] = c;
+    if (c < k_cap && level[slot] > thr_bits + 1u) cand_count[slot] = 0;
 }
+
+#define NS_LIST_CAP 6144   // listed pixels per region kept as a list; a denser region is walked pixel by pixel instead
+#define NS_SURV_CAP 4096   // survivors of one 64x64 tile (every pixel of a tied plateau survives)
 
 __device__ __forceinline__ unsigned ns_getbit(const unsigned* m, int y, int x) { return (m[y * NS_WORDS + (x >> 5)] >> (x & 31)) & 1u; }
 
-// 9x9 dilation of bit mask `in` into `out` (rows of 4 words), `tmp` holds the horizontal pass
-__device__ __forceinline__ void ns_dilate(const unsigned* __restrict__ in, unsigned* __restrict__ tmp, unsigned* __restrict__ out) {
-    for (int y = threadIdx.x; y < NS_REG; y += NS_THREADS) {
-        unsigned r[4], a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = in[y * NS_WORDS + i];
-        auto shl = [](const unsigned x[4], int s, unsigned o[4]) {
-            o[0] = x[0] << s;
-#pragma unroll
-            for (int i = 1; i < 4; ++i) o[i] = (x[i] << s) | (x[i - 1] >> (32 - s));
-        };
-        shl(r, 1, a);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= r[i];
-        shl(a, 2, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= b[i];
-        shl(a, 4, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= b[i];
-        shl(r, 8, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= b[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tmp[y * NS_WORDS + i] = (a[i] >> 4) | (i < 3 ? (a[i + 1] << 28) : 0u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NS_REG * NS_WORDS; i += NS_THREADS) {
-        const int y = i / NS_WORDS, wdx = i % NS_WORDS;
-        const int lo = max(y - 4, 0), hi = min(y + 4, NS_REG - 1);
-        unsigned acc = 0;
-        for (int yy = lo; yy <= hi; ++yy) acc |= tmp[yy * NS_WORDS + wdx];
-        out[i] = acc;
-    }
-}
+struct NsRegion {
+    const float* S;            // [NS_REG][NS_PITCH] scores at or above the level, 0 elsewhere
+    unsigned* MAXM;            // max_mask
+    unsigned* SUPA;            // supp_mask after the initial maxima       = dilate(max_mask_0)
+    unsigned* SUPB;            // added by the maxima of refinement round 1 = dilate(new maxima of round 1)
+    const unsigned short* list;
+    unsigned short* surv;
+    int* n_surv;
+    int n;                     // listed pixels (> NS_LIST_CAP: walk the region densely)
+};
 
-// is listed pixel (ly, lx) with score s >= every (unsuppressed) pixel of its 9x9 window?  3x3 ring first.
-template <bool USE_SUP>
-__device__ __forceinline__ bool ns_window_max(const float* __restrict__ S, const unsigned* __restrict__ SUP, int ly, int lx, float s) {
-    const int y_lo = max(ly - 4, 0), y_hi = min(ly + 4, NS_REG - 1), x_lo = max(lx - 4, 0), x_hi = min(lx + 4, NS_REG - 1);
-    // 3x3 ring (always inside the region for the positions that matter: callers restrict ly, lx to [4, 100))
+// One pass over the listed pixels of a region.  Each lane ring-checks its own pixel (3x3: no larger unsuppressed direct
+// neighbour), then the WARP scans the 9x9 window of every pixel that passed (81 positions over 32 lanes, one vote).
+// A new maximum sets its max_mask bit, ORs its 9x9 block into `sup_out` (the dilation simple_nms applies to the mask,
+// built incrementally) and, inside the output tile, joins the survivor list.
+// ROUND 0: plain window max.  ROUND 1: suppressed = SUPA.  ROUND 2: suppressed = SUPA | SUPB.
+template <int ROUND>
+__device__ __forceinline__ void ns_mark_maxima(const NsRegion& R, unsigned* __restrict__ sup_out, int lo, int hi) {
+    const int lane = threadIdx.x & 31;
+    const bool dense = R.n > NS_LIST_CAP;
+    const int count = dense ? NS_REG * NS_REG : R.n;
+    auto suppressed = [&](int y, int x) -> bool {
+        if (ROUND == 0) return false;
+        unsigned wv = R.SUPA[y * NS_WORDS + (x >> 5)];
+        if (ROUND == 2) wv |= R.SUPB[y * NS_WORDS + (x >> 5)];
+        return (wv >> (x & 31)) & 1u;
+    };
+    for (int e0 = (threadIdx.x >> 5) * 32; e0 < count; e0 += NS_THREADS) {
+        const int e = e0 + lane;
+        int ly = 0, lx = 0;
+        float s = 0.f;
+        bool cand = false;
+        if (e < count) {
+            if (dense) { ly = e / NS_REG; lx = e - ly * NS_REG; } else { ly = R.list[e] >> 8; lx = R.list[e] & 255; }
+            if (ly >= lo && ly < hi && lx >= lo && lx < hi) {
+                s = R.S[ly * NS_PITCH + lx];
+                cand = s > 0.f && !suppressed(ly, lx);
+                if (cand) {
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
+                    for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            if (dy == 0 && dx == 0) continue;
-            const int yy = ly + dy, xx = lx + dx;
-            if (S[yy * NS_PITCH + xx] > s && !(USE_SUP && ns_getbit(SUP, yy, xx))) return false;
+                        for (int dx = -1; dx <= 1; ++dx)
+                            if ((dy | dx) != 0 && R.S[(ly + dy) * NS_PITCH + lx + dx] > s && !suppressed(ly + dy, lx + dx)) cand = false;
+                }
+            }
         }
-    for (int yy = y_lo; yy <= y_hi; ++yy) {
-        const float* row = S + yy * NS_PITCH;
-        for (int xx = x_lo; xx <= x_hi; ++xx)
-            if (row[xx] > s && !(USE_SUP && ns_getbit(SUP, yy, xx))) return false;
+        unsigned todo = __ballot_sync(0xffffffffu, cand);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int cy = __shfl_sync(0xffffffffu, ly, src), cx = __shfl_sync(0xffffffffu, lx, src);
+            const float cs = __shfl_sync(0xffffffffu, s, src);
+            bool bad = false;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int p = lane + 32 * r;   // window position 0..80
+                if (p < 81) {
+                    const int yy = cy + p / 9 - 4, xx = cx + p % 9 - 4;
+                    if (yy >= 0 && yy < NS_REG && xx >= 0 && xx < NS_REG && R.S[yy * NS_PITCH + xx] > cs && !suppressed(yy, xx)) bad = true;
+                }
+            }
+            if (__any_sync(0xffffffffu, bad)) continue;
+            if (lane == 0) {
+                atomicOr(&R.MAXM[cy * NS_WORDS + (cx >> 5)], 1u << (cx & 31));
+                if (cy >= 20 && cy < 20 + NS_TILE && cx >= 20 && cx < 20 + NS_TILE) {
+                    const int pos = atomicAdd(R.n_surv, 1);
+                    if (pos < NS_SURV_CAP) R.surv[pos] = (unsigned short)((cy << 8) | cx);
+                }
+            }
+            if (sup_out && lane < 9) {   // rows cy - 4 .. cy + 4, columns cx - 4 .. cx + 4 (clipped to the region)
+                const int yy = cy - 4 + lane;
+                if (yy >= 0 && yy < NS_REG) {
+                    const int x_lo = max(cx - 4, 0), x_hi = min(cx + 4, NS_REG - 1);
+                    const int w0 = x_lo >> 5, w1 = x_hi >> 5;
+                    const unsigned m_lo = 0xffffffffu << (x_lo & 31), m_hi = 0xffffffffu >> (31 - (x_hi & 31));
+                    if (w0 == w1) atomicOr(&sup_out[yy * NS_WORDS + w0], m_lo & m_hi);
+                    else { atomicOr(&sup_out[yy * NS_WORDS + w0], m_lo); atomicOr(&sup_out[yy * NS_WORDS + w1], m_hi); }
+                }
+            }
+        }
     }
-    return true;
 }
 
-__global__ void __launch_bounds__(NS_THREADS) nms_sparse_kernel(const float* __restrict__ score, int h, int w, int n_img, float threshold, int border,
-                                                                int slot0, const unsigned* __restrict__ level, const int* __restrict__ flag,
-                                                                int only_flagged, unsigned long long* __restrict__ cand_keys,
+__global__ void __launch_bounds__(NS_THREADS, 3) nms_sparse_kernel(const float* __restrict__ score, int h, int w, int n_img, float threshold, int border,
+                                                                int slot0, const unsigned* __restrict__ level, const int* __restrict__ first_count,
+                                                                int redo, int k_cap, unsigned thr_bits, unsigned long long* __restrict__ cand_keys,
                                                                 int* __restrict__ cand_count) {
     extern __shared__ float sm[];
-    float* S = sm;                                                       // scores at or above the level, 0 elsewhere
-    unsigned* ACT = reinterpret_cast<unsigned*>(S + NS_REG * NS_PITCH);  // listed pixels
-    unsigned* MAXM = ACT + NS_REG * NS_WORDS;                            // max_mask
-    unsigned* SUP = MAXM + NS_REG * NS_WORDS;                            // supp_mask
-    unsigned* TMP = SUP + NS_REG * NS_WORDS;
-    unsigned short* list = reinterpret_cast<unsigned short*>(TMP + NS_REG * NS_WORDS);   // [NS_REG * NS_REG] (ly << 8 | lx)
-    __shared__ int n_act;
+    float* S = sm;
+    unsigned* MAXM = reinterpret_cast<unsigned*>(S + NS_REG * NS_PITCH);
+    unsigned* SUPA = MAXM + NS_REG * NS_WORDS;
+    unsigned* SUPB = SUPA + NS_REG * NS_WORDS;
+    unsigned short* list = reinterpret_cast<unsigned short*>(SUPB + NS_REG * NS_WORDS);   // [NS_LIST_CAP] (ly << 8 | lx)
+    unsigned short* surv = list + NS_LIST_CAP;                                            // [NS_SURV_CAP]
+    __shared__ int n_act, n_surv;
     const int tiles_x = (w + NS_TILE - 1) / NS_TILE, tiles_y = (h + NS_TILE - 1) / NS_TILE;
     const int tiles = tiles_x * tiles_y, items = tiles * n_img;
     const int lane = threadIdx.x & 31;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / tiles, t = item - b * tiles;
         const int slot = slot0 + b;
-        if (only_flagged && !flag[slot]) continue;
-        const unsigned lv = level[slot];
+        unsigned lv = level[slot];
+        if (redo) {
+            // second launch: only images whose first pass found fewer than K survivors above a level that was higher than
+            // the plain threshold are redone, from the threshold (first_count / level are not written by this launch)
+            if (!(first_count[slot] < k_cap && lv > thr_bits + 1u)) continue;
+            lv = thr_bits + 1u;
+        }
         const int y0 = (t / tiles_x) * NS_TILE - 20, x0 = (t % tiles_x) * NS_TILE - 20;
         const float* sc = score + (size_t)b * h * w;
         __syncthreads();   // previous item's shared memory is no longer read
-        if (threadIdx.x == 0) n_act = 0;
-        for (int i = threadIdx.x; i < NS_REG * NS_WORDS; i += NS_THREADS) MAXM[i] = 0u;
+        if (threadIdx.x == 0) { n_act = 0; n_surv = 0; }
+        for (int i = threadIdx.x; i < 3 * NS_REG * NS_WORDS; i += NS_THREADS) MAXM[i] = 0u;   // MAXM, SUPA, SUPB are contiguous
         __syncthreads();
-        // ---- load: one slot per (row, column < 128); a warp covers one mask word
-        for (int i = threadIdx.x; i < NS_REG * 128; i += NS_THREADS) {
-            const int ly = i >> 7, lx = i & 127;
-            const int y = y0 + ly, x = x0 + lx;
-            float v = 0.f;
-            bool act = false;
-            if (lx < NS_REG && y >= 0 && y < h && x >= 0 && x < w) {
-                v = __ldg(&sc[(size_t)y * w + x]);
-                act = (int)__float_as_uint(v) >= (int)lv;
+        // ---- load.  Fast path (row pitch a multiple of 4 pixels): the region row is 26 aligned float4 (x0 = 64 t - 20 is a
+        // multiple of 4, so a vector is entirely inside or outside the image); every thread issues all of its loads
+        // before the first use, then compacts its listed pixels with one warp scan + one atomicAdd per warp.
+        if ((w & 3) == 0) {
+            constexpr int V = NS_REG / 4;                                   // 26 vectors per row
+            constexpr int PER = (NS_REG * V + NS_THREADS - 1) / NS_THREADS;  // 11
+            float4 v[PER];
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int idx = u * NS_THREADS + threadIdx.x;
+                const int ly = idx / V, c4 = idx - ly * V;
+                const int y = y0 + ly, x = x0 + 4 * c4;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < NS_REG * V && y >= 0 && y < h && x >= 0 && x < w) v[u] = __ldg(reinterpret_cast<const float4*>(&sc[(size_t)y * w + x]));
             }
-            if (lx < NS_REG) S[ly * NS_PITCH + lx] = act ? v : 0.f;
-            const unsigned ballot = __ballot_sync(0xffffffffu, act);
-            if (lane == 0) ACT[ly * NS_WORDS + (lx >> 5)] = ballot;
-            if (ballot) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&n_act, __popc(ballot));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (act) list[base + __popc(ballot & ((1u << lane) - 1))] = (unsigned short)((ly << 8) | lx);
-            }
-        }
-        __syncthreads();
-        const int n = n_act;
-        if (n == 0) continue;   // uniform: nothing at or above the level in this region
-        // ---- max_mask = (score == 9x9 max), needed on [4, 100)^2
-        for (int e = threadIdx.x; e < n; e += NS_THREADS) {
-            const int ly = list[e] >> 8, lx = list[e] & 255;
-            if (ly < 4 || ly >= NS_REG - 4 || lx < 4 || lx >= NS_REG - 4) continue;
-            if (ns_window_max<false>(S, nullptr, ly, lx, S[ly * NS_PITCH + lx])) atomicOr(&MAXM[ly * NS_WORDS + (lx >> 5)], 1u << (lx & 31));
-        }
-        __syncthreads();
-        // ---- two refinement rounds: supp = dilate(max); new maxima among the unsuppressed
-#pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
-            ns_dilate(MAXM, TMP, SUP);
-            __syncthreads();
-            const int lo = it == 0 ? 12 : 20, hi = NS_REG - lo;   // where this round's result is still needed / valid
-            for (int e = threadIdx.x; e < n; e += NS_THREADS) {
-                const int ly = list[e] >> 8, lx = list[e] & 255;
-                if (ly < lo || ly >= hi || lx < lo || lx >= hi) continue;
-                if (ns_getbit(SUP, ly, lx)) continue;   // suppressed (covers every pixel that is already a maximum)
-                if (ns_window_max<true>(S, SUP, ly, lx, S[ly * NS_PITCH + lx])) atomicOr(&MAXM[ly * NS_WORDS + (lx >> 5)], 1u << (lx & 31));
-            }
-            __syncthreads();
-        }
-        // ---- emit the survivors of the central tile
-        for (int e0 = 0; e0 < n; e0 += NS_THREADS) {
-            const int e = e0 + threadIdx.x;
-            bool keep = false;
-            float s = 0.f;
-            int y = 0, x = 0;
-            if (e < n) {
-                const int ly = list[e] >> 8, lx = list[e] & 255;
-                y = y0 + ly; x = x0 + lx;
-                if (ly >= 20 && ly < 20 + NS_TILE && lx >= 20 && lx < 20 + NS_TILE && ns_getbit(MAXM, ly, lx)) {
-                    s = S[ly * NS_PITCH + lx];
-                    keep = s > threshold && y >= border && y < h - border && x >= border && x < w - border;
+            unsigned long long bits = 0ull;
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int idx = u * NS_THREADS + threadIdx.x;
+                if (idx < NS_REG * V) {
+                    const int ly = idx / V, c4 = idx - ly * V;
+                    float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool act = (int)__float_as_uint(f[j]) >= (int)lv;
+                        if (act) { bits |= 1ull << (4 * u + j); ++cnt; } else f[j] = 0.f;
+                    }
+                    float* dst = S + ly * NS_PITCH + 4 * c4;
+                    dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2]; dst[3] = f[3];
                 }
             }
-            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int leader = __ffs(ballot) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&cand_count[slot], __popc(ballot));
-                base = __shfl_sync(ballot, base, leader);
-                const int pos = base + __popc(ballot & ((1u << lane) - 1));
-                if (pos < GNB_CAND_CAP)
-                    cand_keys[(size_t)slot * GNB_CAND_CAP + pos] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(s)) << 32) | (unsigned)(y * w + x);
+            int incl = cnt;   // inclusive warp scan of the per-thread counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t2;
+            }
+            const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (lane == 31 && warp_total) base = atomicAdd(&n_act, warp_total);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+            while (bits) {
+                const int bpos = __ffsll((long long)bits) - 1;
+                bits &= bits - 1ull;
+                const int idx = (bpos >> 2) * NS_THREADS + threadIdx.x;
+                const int ly = idx / V, c4 = idx - ly * V;
+                if (base < NS_LIST_CAP) list[base] = (unsigned short)((ly << 8) | (4 * c4 + (bpos & 3)));
+                ++base;
+            }
+        } else {
+            for (int i = threadIdx.x; i < NS_REG * 128; i += NS_THREADS) {
+                const int ly = i >> 7, lx = i & 127;
+                const int y = y0 + ly, x = x0 + lx;
+                float v = 0.f;
+                bool act = false;
+                if (lx < NS_REG && y >= 0 && y < h && x >= 0 && x < w) {
+                    v = __ldg(&sc[(size_t)y * w + x]);
+                    act = (int)__float_as_uint(v) >= (int)lv;
+                }
+                if (lx < NS_REG) S[ly * NS_PITCH + lx] = act ? v : 0.f;
+                const unsigned ballot = __ballot_sync(0xffffffffu, act);
+                if (ballot) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&n_act, __popc(ballot));
+                    base = __shfl_sync(0xffffffffu, base, 0) + __popc(ballot & ((1u << lane) - 1));
+                    if (act && base < NS_LIST_CAP) list[base] = (unsigned short)((ly << 8) | lx);
+                }
+            }
+        }
+        __syncthreads();
+        NsRegion R{S, MAXM, SUPA, SUPB, list, surv, &n_surv, n_act};
+        if (R.n == 0) continue;   // uniform: nothing at or above the level in this region
+        // ---- simple_nms: max_mask = (score == 9x9 max) on [4, 100)^2, then two refinement rounds, each valid on a region
+        // 8 px smaller; the supp masks are the dilations of the maxima found so far, built by the finder itself.  A pixel of
+        // the (scores > 0) list can only lose to a LARGER unsuppressed pixel, so "ties survive" exactly as == does upstream.
+        ns_mark_maxima<0>(R, SUPA, 4, NS_REG - 4);
+        __syncthreads();
+        ns_mark_maxima<1>(R, SUPB, 12, NS_REG - 12);
+        __syncthreads();
+        ns_mark_maxima<2>(R, nullptr, 20, NS_REG - 20);
+        __syncthreads();
+        // ---- emit the survivors of the output tile (a maximum stays one: each was listed when it was found)
+        const int ns = n_surv;
+        if (ns <= NS_SURV_CAP) {
+            if (threadIdx.x < 32 && ns > 0) {
+                for (int e0 = 0; e0 < ns; e0 += 32) {
+                    const int e = e0 + lane;
+                    bool keep = false;
+                    float sv = 0.f;
+                    int y = 0, x = 0;
+                    if (e < ns) {
+                        const int ly = surv[e] >> 8, lx = surv[e] & 255;
+                        y = y0 + ly; x = x0 + lx;
+                        sv = S[ly * NS_PITCH + lx];
+                        keep = sv > threshold && y >= border && y < h - border && x >= border && x < w - border;
+                    }
+                    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                    if (ballot) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&cand_count[slot], __popc(ballot));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const int pos = base + __popc(ballot & ((1u << lane) - 1));
+                        if (keep && pos < GNB_CAND_CAP)
+                            cand_keys[(size_t)slot * GNB_CAND_CAP + pos] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(sv)) << 32) | (unsigned)(y * w + x);
+                    }
+                }
+            }
+        } else {
+            // survivor list overflow (a large tied plateau): walk the tile's max_mask instead
+            for (int i0 = 0; i0 < NS_TILE * NS_TILE; i0 += NS_THREADS) {
+                const int i = i0 + threadIdx.x;
+                const int ly = i / NS_TILE + 20, lx = i % NS_TILE + 20;
+                const int y = y0 + ly, x = x0 + lx;
+                const float sv = S[ly * NS_PITCH + lx];
+                const bool keep = ns_getbit(MAXM, ly, lx) && sv > threshold && y >= border && y < h - border && x >= border && x < w - border;
+                const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                if (ballot) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&cand_count[slot], __popc(ballot));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const int pos = base + __popc(ballot & ((1u << lane) - 1));
+                    if (keep && pos < GNB_CAND_CAP)
+                        cand_keys[(size_t)slot * GNB_CAND_CAP + pos] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(sv)) << 32) | (unsigned)(y * w + x);
+                }
             }
         }
     }
@@ -674,19 +775,23 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         const unsigned thr_bits = __float_as_uint_host(ctx->cfg.keypoint_threshold);
         const unsigned target = (unsigned)((32ll * k_cap + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP);
         const int rows = ceil_div(h, NS_HIST_ROW_STEP);
-        dim3 hgrid(min(ceil_div(rows * w, 256 * 8), 64), 1, n);
+        dim3 hgrid(min(ceil_div(rows * w, 256 * 4), 128), 1, n);
         GNB_KERNEL(ctx, "nms_hist_kernel", nms_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(score, h, w, thr_bits, slot0, ctx->nms_hist));
         GNB_KERNEL(ctx, "nms_level_kernel", nms_level_kernel<<<n, 32, 0, ctx->stream>>>(ctx->nms_hist, slot0, target, thr_bits, ctx->nms_level, ctx->nms_flag));
-        const size_t smem = (size_t)NS_REG * NS_PITCH * sizeof(float) + 4 * NS_REG * NS_WORDS * sizeof(unsigned) + (size_t)NS_REG * NS_REG * sizeof(unsigned short);
+        const size_t smem = (size_t)NS_REG * NS_PITCH * sizeof(float) + 3 * NS_REG * NS_WORDS * sizeof(unsigned) +
+                            (size_t)(NS_LIST_CAP + NS_SURV_CAP) * sizeof(unsigned short);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_sparse_kernel, (int)smem));
         const int items = ceil_div(w, NS_TILE) * ceil_div(h, NS_TILE) * n;
         const int grid = min(items, ctx->sm_count * 3);
         GNB_KERNEL(ctx, "nms_sparse_kernel", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
-            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 0, ctx->cand_keys, ctx->cand_count));
-        GNB_KERNEL(ctx, "nms_check_kernel", nms_check_kernel<<<ceil_div(n, 64), 64, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->cand_count,
-                                                                                              ctx->nms_level, ctx->nms_flag));
+            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, nullptr, 0, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
+        // exact redo, from the plain threshold, of the images with fewer than K survivors above their level (rare); its
+        // CTAs decide from the first pass's counts (copied aside: the redo resets and refills cand_count) and exit at once
+        // when there is nothing to redo
+        GNB_KERNEL(ctx, "nms_redo_prepare", nms_redo_prepare<<<ceil_div(n, 64), 64, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->nms_level, ctx->cand_count,
+                                                                                               ctx->nms_flag));
         GNB_KERNEL(ctx, "nms_sparse_kernel(redo)", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
-            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 1, ctx->cand_keys, ctx->cand_count));
+            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 1, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
     } else if (ctx->cfg.nms_radius == 4) {
         const size_t smem = (size_t)N4_REG * N4_PITCH * 2 * sizeof(float) + 3 * N4_REG * N4_WORDS * sizeof(unsigned);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_r4_kernel, (int)smem));
