@@ -81,10 +81,11 @@ SIGNATURES = {
     "gnb_matcher_layers": (_I, [_VP]),
     "gnb_match_lightglue": (_I, [_VP, _VP, _VP, _I, _F, _F, _VP, _VP, _I, _F, _F, _I, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_refined_descriptors": (_I, [_VP, _I, _VP, _I]),
-    "gnb_knn_ratio_match": (_I, [_VP, _VP, _I, _VP, _I, _I, _F, _VP, _VP, _I, C.POINTER(_I)]),
+    "gnb_knn_ratio_match": (_I, [_VP, _VP, _I, _VP, _I, _I, C.c_double, _I, _VP, _VP, _I, C.POINTER(_I)]),
     "gnb_solve_pnp": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, C.POINTER(_I)]),
     "gnb_geodetic_tail": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),
     "gnb_pose_batch": (_I, [_VP, _I, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, C.POINTER(GnbPoseResult)]),
+    "gnb_pose_from_records": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, C.POINTER(GnbPoseResult)]),
     "gnb_pose_candidates": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, C.POINTER(GnbPoseResult), C.POINTER(_I)]),
     "gnb_cache_clear": (_I, [_VP]),
     "gnb_rotate_crop": (_I, [_VP, _VP, _I, _VP, _I, _I, C.c_double, _I, _I, _I, _VP, _VP, _VP, _VP]),

@@ -3,8 +3,17 @@
 // and the stage-isolated hooks used by the parity tests.
 #include "common.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <new>
 #include <vector>
+
+// NVTX range around a stage of the path (K1 dense stack, K2/K3 keypoints, K4 matcher, K5/K6 PnP + tail): visible in
+// Nsight Systems / ncu --nvtx; a no-op push/pop when no tool is attached
+struct GnbRange {
+    explicit GnbRange(const char* name) { nvtxRangePushA(name); }
+    ~GnbRange() { nvtxRangePop(); }
+};
 
 static char g_create_err[512] = "";
 
@@ -286,28 +295,39 @@ extern "C" int gnb_create(const gnb_config* cfg, const void* weights, size_t nby
         GNB_SET_ERR(ctx, "stream create failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(GNB_E_CUDA);
     }
-    // weight blob: 16-byte header + floats (gisnav_b200/weights.py)
-    std::vector<uint8_t> blob(nbytes);
-    if (weights_on_device) {
-        if (cudaMemcpy(blob.data(), weights, nbytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
-            GNB_SET_ERR(ctx, "cannot read weights from device");
-            return fail(GNB_E_CUDA);
-        }
-    } else {
-        memcpy(blob.data(), weights, nbytes);
-    }
-    uint32_t hdr[4];
-    if (nbytes < 16) { GNB_SET_ERR(ctx, "weight blob too small"); return fail(GNB_E_INVALID); }
-    memcpy(hdr, blob.data(), 16);
+    // weight blob: 16-byte header + floats (gisnav_b200/weights.py).  The floats are repacked ON THE DEVICE
+    // (gnb_conv_init / gnb_match_init launch the repack kernels): a blob that arrived by NCCL broadcast is consumed
+    // where it lies, a host blob is copied once.
     const size_t expect_floats = 1366914;
-    if (memcmp(blob.data(), "GNBW", 4) != 0 || hdr[1] != 1 || hdr[2] != expect_floats || nbytes != 16 + 4 * expect_floats) {
+    if (nbytes != 16 + 4 * expect_floats) { GNB_SET_ERR(ctx, "bad weight blob size %zu (expected %zu)", nbytes, 16 + 4 * expect_floats); return fail(GNB_E_INVALID); }
+    uint32_t hdr[4];
+    if (cudaMemcpy(hdr, weights, 16, weights_on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess) {
+        GNB_SET_ERR(ctx, "cannot read the weight blob header");
+        return fail(GNB_E_CUDA);
+    }
+    if (memcmp(hdr, "GNBW", 4) != 0 || hdr[1] != 1 || hdr[2] != expect_floats) {
         GNB_SET_ERR(ctx, "bad weight blob (magic/version/size)");
         return fail(GNB_E_INVALID);
     }
-    const float* fl = reinterpret_cast<const float*>(blob.data() + 16);
-    if ((rc = gnb_conv_init(ctx, fl))) return fail(rc);
+    const float* fl = nullptr;   // device pointer to the blob's floats
+    float* staged = nullptr;
+    if (weights_on_device) {
+        fl = reinterpret_cast<const float*>(static_cast<const uint8_t*>(weights) + 16);
+    } else {
+        if (cudaMalloc(&staged, 4 * expect_floats) != cudaSuccess ||
+            cudaMemcpy(staged, static_cast<const uint8_t*>(weights) + 16, 4 * expect_floats, cudaMemcpyHostToDevice) != cudaSuccess) {
+            GNB_SET_ERR(ctx, "cannot stage the weight blob on the device");
+            if (staged) cudaFree(staged);
+            return fail(GNB_E_CUDA);
+        }
+        fl = staged;
+    }
+    rc = gnb_conv_init(ctx, fl);
     const float* head = fl + (expect_floats - (256 * 256 + 256 + 256 + 1));
-    if ((rc = gnb_match_init(ctx, head, head + 256 * 256, head + 256 * 256 + 256, head[256 * 256 + 512]))) return fail(rc);
+    if (!rc) rc = gnb_match_init(ctx, head, head + 256 * 256, head + 256 * 256 + 256, head + 256 * 256 + 512);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) { GNB_SET_ERR(ctx, "weight repack failed: %s", cudaGetErrorString(cudaGetLastError())); rc = GNB_E_CUDA; }
+    if (staged) cudaFree(staged);
+    if (rc) return fail(rc);
     if ((rc = alloc_workspace(ctx))) return fail(rc);
     if ((cfg->conv_impl == 0 || cfg->precision == 1) && (rc = gnb_conv_tc_init(ctx))) return fail(rc);
     if (cfg->match_impl == 0 && (rc = gnb_match_tc_init(ctx))) return fail(rc);
@@ -455,8 +475,8 @@ static int match_impl(gnb_ctx* ctx, const float* desc_a, int n_a, const float* d
 }
 
 // TwistNode's matcher: brute-force 2-NN + ratio test (twist_node.py:248,263-267)
-extern "C" int gnb_knn_ratio_match(gnb_ctx* ctx, const float* desc_q, int n_q, const float* desc_r, int n_r, int dim, float ratio,
-                                   int64_t* out_idx, float* out_dist, int cap, int* n_out) {
+extern "C" int gnb_knn_ratio_match(gnb_ctx* ctx, const float* desc_q, int n_q, const float* desc_r, int n_r, int dim, double ratio,
+                                   int on_device, int64_t* out_idx, float* out_dist, int cap, int* n_out) {
     if (!ctx || !n_out) return GNB_E_INVALID;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     *n_out = 0;
@@ -465,25 +485,36 @@ extern "C" int gnb_knn_ratio_match(gnb_ctx* ctx, const float* desc_q, int n_q, c
     const int k = ctx->cfg.max_keypoints;
     if (n_q > k || n_r > k) { GNB_SET_ERR(ctx, "descriptor count exceeds max_keypoints=%d", k); return GNB_E_CAPACITY; }
     if (ctx->cfg.match_impl != 0) { GNB_SET_ERR(ctx, "gnb_knn_ratio_match needs the tcgen05 matcher (match_impl = 0)"); return GNB_E_INVALID; }
+    GnbRange range("gnb_knn_ratio_match");
     int rc;
-    if ((rc = gnb_ensure_stage(ctx, (size_t)n_q * dim, (size_t)n_r * dim))) return rc;
-    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_a, desc_q, sizeof(float) * n_q * dim, cudaMemcpyHostToDevice, ctx->stream));
-    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_b, desc_r, sizeof(float) * n_r * dim, cudaMemcpyHostToDevice, ctx->stream));
+    const float *dq = desc_q, *dr = desc_r;
+    if (!on_device) {
+        if ((rc = gnb_ensure_stage(ctx, (size_t)n_q * dim, (size_t)n_r * dim))) return rc;
+        GNB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_a, desc_q, sizeof(float) * n_q * dim, cudaMemcpyHostToDevice, ctx->stream));
+        GNB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_b, desc_r, sizeof(float) * n_r * dim, cudaMemcpyHostToDevice, ctx->stream));
+        dq = ctx->stage_a; dr = ctx->stage_b;
+    }
     const int sb = ctx->cfg.max_batch;
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n_q, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count + sb, &n_r, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     GNB_SYNC(ctx);
-    if ((rc = gnb_knn_ratio(ctx, ctx->stage_a, n_q, ctx->stage_b, n_r, dim, (double)ratio))) return rc;
+    if ((rc = gnb_knn_ratio(ctx, dq, n_q, dr, n_r, dim, ratio))) return rc;
     int n = 0;
     if ((rc = read_count(ctx, ctx->match_count, &n))) return rc;
     n = n < cap ? n : cap;
     *n_out = n;
     if (n > 0) {
-        std::vector<int> tmp(2 * n);
-        GNB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->match_idx, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_dist) GNB_CUDA(ctx, cudaMemcpyAsync(out_dist, ctx->match_score, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        GNB_SYNC(ctx);
-        if (out_idx) for (int i = 0; i < 2 * n; ++i) out_idx[i] = tmp[i];
+        if (on_device) {
+            if (out_idx) GNB_KERNEL(ctx, "widen_idx_kernel", widen_idx_kernel<<<ceil_div(2 * n, 256), 256, 0, ctx->stream>>>(ctx->match_idx, (long long*)out_idx, 2 * n));
+            if (out_dist) GNB_CUDA(ctx, cudaMemcpyAsync(out_dist, ctx->match_score, sizeof(float) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+            GNB_SYNC(ctx);
+        } else {
+            std::vector<int> tmp(2 * n);
+            GNB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->match_idx, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_dist) GNB_CUDA(ctx, cudaMemcpyAsync(out_dist, ctx->match_score, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+            GNB_SYNC(ctx);
+            if (out_idx) for (int i = 0; i < 2 * n; ++i) out_idx[i] = tmp[i];
+        }
     }
     return GNB_OK;
 }
@@ -533,11 +564,26 @@ extern "C" int gnb_geodetic_tail(gnb_ctx* ctx, const double* r9, const double* t
     return gnb_tail_device(ctx, r9, t3, affine12, ref_h, ref_w, out_ecef3, out_quat4, out_lla3);
 }
 
+static int pose_batch_impl(gnb_ctx* ctx, int batch, const uint8_t* frames, int hq, int wq, const uint8_t* tiles, int ht, int wt,
+                           const uint8_t* dems, const double* k9, const double* affine12, int on_device, gnb_pose_result* results);
+
 extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, int hq, int wq, const uint8_t* tiles, int ht,
                               int wt, const uint8_t* dems, const double* k9, const double* affine12, int on_device,
                               gnb_pose_result* results) {
     if (!ctx || !frames || !tiles || !k9 || !affine12 || !results || batch < 1) return GNB_E_INVALID;
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GnbRange range("gnb_pose_batch");
+    const int rc = pose_batch_impl(ctx, batch, frames, hq, wq, tiles, ht, wt, dems, k9, affine12, on_device, results);
+    if (rc < 0) {
+        // an error path must not leave copies of the caller's buffers in flight: the caller may free or reuse them
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    return rc;
+}
+
+static int pose_batch_impl(gnb_ctx* ctx, int batch, const uint8_t* frames, int hq, int wq, const uint8_t* tiles, int ht, int wt,
+                           const uint8_t* dems, const double* k9, const double* affine12, int on_device, gnb_pose_result* results) {
     if (batch > ctx->cfg.max_batch) { GNB_SET_ERR(ctx, "batch %d exceeds max_batch %d", batch, ctx->cfg.max_batch); return GNB_E_CAPACITY; }
     int rc;
     if ((rc = check_image(ctx, hq, wq)) || (rc = check_image(ctx, ht, wt))) return rc;
@@ -558,23 +604,39 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
     // query frames -> slots [0, batch)
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_frames, 0));
     cw.img = cw.img_a;
-    if ((rc = gnb_conv_forward(ctx, batch, hq, wq, 0))) return rc;
-    if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, hq, wq, 0))) return rc;
-    if ((rc = gnb_describe(ctx, batch, hq, wq, 0))) return rc;
+    {
+        GnbRange r1("K1 dense stack (frames)");
+        if ((rc = gnb_conv_forward(ctx, batch, hq, wq, 0))) return rc;
+    }
+    {
+        GnbRange r2("K2+K3 keypoints + descriptors (frames)");
+        if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, hq, wq, 0))) return rc;
+        if ((rc = gnb_describe(ctx, batch, hq, wq, 0))) return rc;
+    }
     // reference rasters -> slots [max_batch, max_batch + batch)
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tiles, 0));
-    cw.img = cw.img_b;
-    rc = gnb_conv_forward(ctx, batch, ht, wt, 0);
-    cw.img = cw.img_a;
-    if (rc) return rc;
-    if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, ht, wt, sb))) return rc;
-    if ((rc = gnb_describe(ctx, batch, ht, wt, sb))) return rc;
+    {
+        GnbRange r1("K1 dense stack (rasters)");
+        cw.img = cw.img_b;
+        rc = gnb_conv_forward(ctx, batch, ht, wt, 0);
+        cw.img = cw.img_a;
+        if (rc) return rc;
+    }
+    {
+        GnbRange r2("K2+K3 keypoints + descriptors (rasters)");
+        if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, ht, wt, sb))) return rc;
+        if ((rc = gnb_describe(ctx, batch, ht, wt, sb))) return rc;
+    }
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_params, 0));
-    // transformer layers of the reference matcher (pose_node.py:109-121), when a layer blob is loaded
-    if ((rc = gnb_lightglue_forward(ctx, batch, 0, sb, (float)hq, (float)wq, (float)ht, (float)wt))) return rc;
-    if ((rc = gnb_match_project(ctx, 0, batch))) return rc;
-    if ((rc = gnb_match_project(ctx, sb, batch))) return rc;
-    if ((rc = gnb_match_pairs(ctx, batch, 0, sb))) return rc;
+    {
+        GnbRange r4("K4 matcher");
+        // transformer layers of the reference matcher (pose_node.py:109-121), when a layer blob is loaded
+        if ((rc = gnb_lightglue_forward(ctx, batch, 0, sb, (float)hq, (float)wq, (float)ht, (float)wt))) return rc;
+        if ((rc = gnb_match_project(ctx, 0, batch))) return rc;
+        if ((rc = gnb_match_project(ctx, sb, batch))) return rc;
+        if ((rc = gnb_match_pairs(ctx, batch, 0, sb))) return rc;
+    }
+    GnbRange r5("K5+K6 PnP/RANSAC + refit + WGS84 tail");
     if ((rc = gnb_pnp_pairs(ctx, batch, ht, wt, dems ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1))) return rc;
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut) * batch, cudaMemcpyDeviceToHost, ctx->stream));
     GNB_SYNC(ctx);
@@ -586,6 +648,67 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
         }
         if (results[b].status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM in pair %d", b); return GNB_E_RANGE; }
     }
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wire-format ingest: the query side of an OrthoStereoImage message arrives as PRE-EXTRACTED keypoints, one packed record
+// per keypoint (x, y, z, size, angle f32 + descriptor f32[D]; KEYPOINT_DTYPE, ros/gisnav/gisnav/core/_shared.py:26-35,
+// decoded with np.frombuffer at pose_node.py:207-213).  The record bytes are copied to the device as they are and
+// unpacked there into keypoint slot 0; the reference raster is extracted on the device as usual.
+__global__ void __launch_bounds__(256) unpack_records_kernel(const float* __restrict__ rec, int n, int step_floats, int desc_dim,
+                                                             float* __restrict__ kp_xy, float* __restrict__ desc) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const float* p = rec + (size_t)r * step_floats;
+    if (lane < 2) kp_xy[r * 2 + lane] = p[lane];
+    for (int c = lane; c < 256; c += 32) desc[(size_t)r * 256 + c] = c < desc_dim ? p[5 + c] : 0.f;
+}
+
+extern "C" int gnb_pose_from_records(gnb_ctx* ctx, const void* records, int n_records, int point_step, int desc_dim, int hq, int wq,
+                                     const uint8_t* reference, int ht, int wt, const uint8_t* dem, const double* k9,
+                                     const double* affine12, gnb_pose_result* result) {
+    if (!ctx || !reference || !k9 || !affine12 || !result || n_records < 0 || (n_records > 0 && !records)) return GNB_E_INVALID;
+    GNB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (desc_dim != GNB_DESC_DIM || point_step != 4 * (5 + desc_dim)) {
+        GNB_SET_ERR(ctx, "records must carry %d-d descriptors with point_step %d (got D=%d, step %d): 128-d SIFT records cannot feed this matcher head",
+                    GNB_DESC_DIM, 4 * (5 + GNB_DESC_DIM), desc_dim, point_step);
+        return GNB_E_INVALID;
+    }
+    const int k = ctx->cfg.max_keypoints, sb = ctx->cfg.max_batch;
+    if (n_records > k) { GNB_SET_ERR(ctx, "%d records exceed max_keypoints=%d", n_records, k); return GNB_E_CAPACITY; }
+    int rc;
+    if ((rc = check_image(ctx, ht, wt))) return rc;
+    GnbRange range("gnb_pose_from_records");
+    ConvWorkspace& cw = ctx->cw;
+    const size_t rec_floats = (size_t)n_records * (point_step / 4);
+    if ((rc = gnb_ensure_stage(ctx, rec_floats ? rec_floats : 1, 0))) return rc;
+    if (n_records) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_a, records, rec_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kp_count, &n_records, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(cw.img_b, reference, (size_t)ht * wt, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->kmat, k9, sizeof(double) * 9, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->affine, affine12, sizeof(double) * 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (dem) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dem, (size_t)ht * wt, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_SYNC(ctx);   // n_records lives on this stack frame
+    if (n_records)
+        GNB_KERNEL(ctx, "unpack_records_kernel", unpack_records_kernel<<<ceil_div(n_records * 32, 256), 256, 0, ctx->stream>>>(
+            ctx->stage_a, n_records, point_step / 4, desc_dim, ctx->kp_xy, ctx->desc_f32));
+    cw.img = cw.img_b;
+    rc = gnb_conv_forward(ctx, 1, ht, wt, 0);
+    cw.img = cw.img_a;
+    if (rc) return rc;
+    if ((rc = gnb_kp_select(ctx, cw.score, 1, ht, wt, sb))) return rc;
+    if ((rc = gnb_describe(ctx, 1, ht, wt, sb))) return rc;
+    if ((rc = gnb_lightglue_forward(ctx, 1, 0, sb, (float)(hq > 0 ? hq : ht), (float)(wq > 0 ? wq : wt), (float)ht, (float)wt))) return rc;
+    if ((rc = gnb_match_project(ctx, 0, 1))) return rc;
+    if ((rc = gnb_match_project(ctx, sb, 1))) return rc;
+    if ((rc = gnb_match_pairs(ctx, 1, 0, sb))) return rc;
+    if ((rc = gnb_pnp_pairs(ctx, 1, ht, wt, dem ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1))) return rc;
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut), cudaMemcpyDeviceToHost, ctx->stream));
+    GNB_SYNC(ctx);
+    pairout_to_result(ctx->out_host[0], result);
+    if (result->n_kp_ref < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); return GNB_E_CAPACITY; }
+    if (result->status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM"); return GNB_E_RANGE; }
     return GNB_OK;
 }
 
@@ -633,6 +756,9 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
     if ((rc = check_image(ctx, hq, wq)) || (rc = check_image(ctx, ht, wt))) return rc;
     const int sb = ctx->cfg.max_batch;
     ConvWorkspace& cw = ctx->cw;
+    GnbRange range("gnb_pose_candidates");
+    // cached features belong to one raster geometry: a different (ht, wt) starts from an empty cache
+    if (ctx->cache_h != ht || ctx->cache_w != wt) { gnb_cache_clear(ctx); ctx->cache_h = ht; ctx->cache_w = wt; }
     // cache lookup: entry[i] = cache entry that will hold raster i's features; hit[i] = already there
     std::vector<int> entry(n_tiles), hit(n_tiles, 0);
     std::vector<char> used(ctx->cache_cap, 0);
@@ -649,7 +775,7 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
         for (int e = 0; e < ctx->cache_cap; ++e)   // least recently used entry not claimed by this call
             if (!used[e] && (best < 0 || ctx->cache_lru[e] < ctx->cache_lru[best])) best = e;
         entry[i] = best; used[best] = 1;
-        ctx->cache_ids[best] = (tile_ids && tile_ids[i] >= 0) ? tile_ids[i] : -1;
+        ctx->cache_ids[best] = -1;   // invalid until the raster has been extracted AND validated (committed after the final sync)
     }
     for (int i = 0; i < n_tiles; ++i) ctx->cache_lru[entry[i]] = ++ctx->cache_clock;
     if (n_cache_hits) *n_cache_hits = hits;
@@ -704,12 +830,16 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
     if ((rc = gnb_pnp_pairs(ctx, n_tiles, ht, wt, dems ? 1 : 0, ht, wt, 1, ctx->cfg.min_matches, 1, stride_a))) return rc;
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, sizeof(PairOut) * n_tiles, cudaMemcpyDeviceToHost, ctx->stream));
     GNB_SYNC(ctx);
+    int err = GNB_OK;
     for (int b = 0; b < n_tiles; ++b) {
         pairout_to_result(ctx->out_host[b], &results[b]);
-        if (results[b].n_kp_qry < 0 || results[b].n_kp_ref < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); return GNB_E_CAPACITY; }
-        if (results[b].status == GNB_E_RANGE) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM in candidate %d", b); return GNB_E_RANGE; }
+        if (results[b].n_kp_qry < 0 || results[b].n_kp_ref < 0) { GNB_SET_ERR(ctx, "NMS candidate buffer overflow"); err = GNB_E_CAPACITY; continue; }
+        // the raster's features are valid: only now does its cache entry get its id (an entry claimed above stays
+        // invalid on every error path, so a later call can never hit half-written features)
+        if (!hit[b] && tile_ids && tile_ids[b] >= 0) ctx->cache_ids[entry[b]] = tile_ids[b];
+        if (results[b].status == GNB_E_RANGE && !err) { GNB_SET_ERR(ctx, "reference keypoint outside the DEM in candidate %d", b); err = GNB_E_RANGE; }
     }
-    return GNB_OK;
+    return err;
 }
 
 // ------------------------------------------------------------------------------------------------

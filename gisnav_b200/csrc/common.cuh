@@ -107,6 +107,7 @@ struct gnb_ctx {
     long long* cache_ids;           // host [cache_cap], -1 = free
     unsigned long long* cache_lru;  // host [cache_cap]
     unsigned long long cache_clock;
+    int cache_h, cache_w;           // raster geometry the cached features belong to
     float* c_kp_xy;                 // [cache_cap][K][2]
     int* c_kp_count;                // [cache_cap]
     bf16* c_mproj;                  // [cache_cap][K][256]
@@ -179,7 +180,7 @@ template <typename F>
 static inline cudaError_t gnb_func_smem(gnb_ctx* ctx, F* func, int bytes) { return gnb_func_smem_impl(ctx, (const void*)func, bytes); }
 
 // ---- stage functions implemented across the .cu files (all enqueue on ctx->stream) -----------
-int gnb_conv_init(gnb_ctx* ctx, const float* blob_floats);  // repack weights
+int gnb_conv_init(gnb_ctx* ctx, const float* blob_floats_dev);  // repack weights (device pointer to the blob's floats)
 void gnb_conv_free(gnb_ctx* ctx);
 // run the dense stack on cw.img (n images of h x w already resident)
 int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc);
@@ -195,7 +196,7 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
 int gnb_kp_sample(gnb_ctx* ctx, const float* dense, int n, int h, int w, int slot0);
 
 // match.cu
-int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const float* m_w, float m_b);
+int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const float* m_w, const float* m_b);  // device pointers into the blob
 void gnb_match_free(gnb_ctx* ctx);
 // project descriptors of `n_slots` consecutive slots
 int gnb_match_project(gnb_ctx* ctx, int slot0, int n_slots);

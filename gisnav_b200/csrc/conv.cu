@@ -10,7 +10,6 @@
 #include "common.cuh"
 
 #include <stdlib.h>
-#include <vector>
 
 struct CUtensorMap_st;
 const CUtensorMap_st* gnb_conv_tc_wmap(gnb_ctx* ctx, int lid);
@@ -23,23 +22,39 @@ int gnb_gemm256_f32(gnb_ctx* ctx, int amode, const void* a, const int* row_idx, 
                     float scale, float* c, int ldc, const char* name);
 int gnb_describe_x3(gnb_ctx* ctx, int n, int h, int w, int slot0);
 
-// ------------------------------------------------------------------------------------------------
-// host-side bf16 rounding (round to nearest even), identical to torch's .to(bfloat16)
-static inline uint16_t f32_to_bf16_bits(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
-    uint32_t lsb = (u >> 16) & 1u;
-    u += 0x7fffu + lsb;
-    return (uint16_t)(u >> 16);
-}
-
 struct LayerSpec { const char* name; int cin, cout, ks; };
 static const LayerSpec kSpecs[GNB_NUM_LAYERS] = {
     {"conv1a", 1, 64, 3},   {"conv1b", 64, 64, 3},   {"conv2a", 64, 64, 3},   {"conv2b", 64, 64, 3},
     {"conv3a", 64, 128, 3}, {"conv3b", 128, 128, 3}, {"conv4a", 128, 128, 3}, {"conv4b", 128, 128, 3},
     {"convPa", 128, 256, 3}, {"convPb", 256, 65, 1}, {"convDa", 128, 256, 3}, {"convDb", 256, 256, 1},
 };
+
+// Weight repack ON THE DEVICE: blob tensor [cout][cin][ks][ks] f32 (PyTorch order) ->
+//   w     bf16 [tap][cout_pad][cin]            (K-major B operand per tap)
+//   w_x3  bf16 [tap][cout_pad][hi: cin | lo: cin]   (fp32-faithful mode: w = hi + lo)
+//   w_f32 f32  [tap][cout_pad][cin]            (fp32-faithful mode, CUDA-core layers)
+// __float2bfloat16_rn is round-to-nearest-even, identical to torch's .to(bfloat16) the oracle uses.
+__global__ void repack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad, bf16* __restrict__ out,
+                                   bf16* __restrict__ out_x3, float* __restrict__ out_f32) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [tap][cout_pad][cin]
+    const size_t total = (size_t)taps * cout_pad * cin;
+    if (i >= total) return;
+    const int ci = (int)(i % cin), co = (int)((i / cin) % cout_pad), t = (int)(i / ((size_t)cin * cout_pad));
+    const float v = co < cout ? w[((size_t)co * cin + ci) * taps + t] : 0.f;
+    const bf16 hi = __float2bfloat16_rn(v);
+    out[i] = hi;
+    if (out_x3) {
+        const size_t row = ((size_t)t * cout_pad + co) * 2 * cin;
+        out_x3[row + ci] = hi;
+        out_x3[row + cin + ci] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+    }
+    if (out_f32) out_f32[i] = v;
+}
+
+__global__ void pad_bias_kernel(const float* __restrict__ b, int cout, int cout_pad, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cout_pad) out[i] = i < cout ? b[i] : 0.f;
+}
 
 int gnb_conv_init(gnb_ctx* ctx, const float* blob) {
     size_t off = 0;
@@ -49,44 +64,18 @@ int gnb_conv_init(gnb_ctx* ctx, const float* blob) {
         L.cin = s.cin; L.cout = s.cout; L.ks = s.ks;
         L.cout_pad = (s.cout + 31) / 32 * 32;  // tcgen05 epilogue reads 32 columns at a time
         const int taps = s.ks * s.ks;
-        const float* w = blob + off;                       // [cout][cin][ks][ks]
+        const float* w = blob + off;                       // [cout][cin][ks][ks] (device)
         const float* b = w + (size_t)s.cout * s.cin * taps;  // [cout]
         off += (size_t)s.cout * s.cin * taps + s.cout;
-        std::vector<uint16_t> wp((size_t)taps * L.cout_pad * s.cin, 0);
-        std::vector<float> bp(L.cout_pad, 0.f);
-        for (int co = 0; co < s.cout; ++co) {
-            bp[co] = b[co];
-            for (int ci = 0; ci < s.cin; ++ci)
-                for (int t = 0; t < taps; ++t)
-                    wp[((size_t)t * L.cout_pad + co) * s.cin + ci] = f32_to_bf16_bits(w[((size_t)co * s.cin + ci) * taps + t]);
-        }
-        GNB_CUDA(ctx, cudaMalloc(&L.w, wp.size() * sizeof(uint16_t)));
-        GNB_CUDA(ctx, cudaMalloc(&L.bias, bp.size() * sizeof(float)));
-        GNB_CUDA(ctx, cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-        GNB_CUDA(ctx, cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const size_t n = (size_t)taps * L.cout_pad * s.cin;
+        GNB_CUDA(ctx, cudaMalloc(&L.w, n * sizeof(bf16)));
+        GNB_CUDA(ctx, cudaMalloc(&L.bias, L.cout_pad * sizeof(float)));
         if (ctx->cfg.precision == 1) {
-            // fp32-faithful mode: w = hi + lo as two bf16 terms per weight ([tap][cout_pad][hi: cin | lo: cin]) for the
-            // tcgen05 layers, and the plain fp32 weights for the CUDA-core layers (conv1a, convPb, convDb)
-            std::vector<uint16_t> wx((size_t)taps * L.cout_pad * 2 * s.cin, 0);
-            std::vector<float> wf((size_t)taps * L.cout_pad * s.cin, 0.f);
-            for (int co = 0; co < s.cout; ++co)
-                for (int ci = 0; ci < s.cin; ++ci)
-                    for (int t = 0; t < taps; ++t) {
-                        const float v = w[((size_t)co * s.cin + ci) * taps + t];
-                        const uint16_t hb = f32_to_bf16_bits(v);
-                        uint32_t hu = (uint32_t)hb << 16;
-                        float hf;
-                        memcpy(&hf, &hu, 4);
-                        const size_t row = ((size_t)t * L.cout_pad + co) * 2 * s.cin;
-                        wx[row + ci] = hb;
-                        wx[row + s.cin + ci] = f32_to_bf16_bits(v - hf);
-                        wf[((size_t)t * L.cout_pad + co) * s.cin + ci] = v;
-                    }
-            GNB_CUDA(ctx, cudaMalloc(&L.w_x3, wx.size() * sizeof(uint16_t)));
-            GNB_CUDA(ctx, cudaMalloc(&L.w_f32, wf.size() * sizeof(float)));
-            GNB_CUDA(ctx, cudaMemcpy(L.w_x3, wx.data(), wx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-            GNB_CUDA(ctx, cudaMemcpy(L.w_f32, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
+            GNB_CUDA(ctx, cudaMalloc(&L.w_x3, 2 * n * sizeof(bf16)));
+            GNB_CUDA(ctx, cudaMalloc(&L.w_f32, n * sizeof(float)));
         }
+        GNB_KERNEL(ctx, "repack_conv_kernel", repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(w, s.cout, s.cin, taps, L.cout_pad, L.w, L.w_x3, L.w_f32));
+        GNB_KERNEL(ctx, "pad_bias_kernel", pad_bias_kernel<<<ceil_div(L.cout_pad, 128), 128, 0, ctx->stream>>>(b, s.cout, L.cout_pad, L.bias));
     }
     return GNB_OK;
 }

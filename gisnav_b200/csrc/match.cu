@@ -13,40 +13,34 @@
 #include "common.cuh"
 
 #include <math.h>
-#include <vector>
 
-static inline uint16_t f2bf_bits(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    uint32_t lsb = (u >> 16) & 1u;
-    u += 0x7fffu + lsb;
-    return (uint16_t)(u >> 16);
+// matcher head weights, repacked on the device from the blob: W bf16 [out][in] and its transpose [in][out], w_m bf16
+__global__ void repack_match_kernel(const float* __restrict__ w, const float* __restrict__ mw, bf16* __restrict__ out_w, bf16* __restrict__ out_wt,
+                                    bf16* __restrict__ out_mw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 256 * 256) return;
+    const int o = i >> 8, in = i & 255;
+    const bf16 v = __float2bfloat16_rn(w[i]);
+    out_w[i] = v;
+    out_wt[in * 256 + o] = v;
+    if (i < 256) out_mw[i] = __float2bfloat16_rn(mw[i]);
 }
 
-
-int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const float* m_w, float m_b) {
-    std::vector<uint16_t> w(256 * 256), wt(256 * 256), mw(256);
-    for (int o = 0; o < 256; ++o)
-        for (int i = 0; i < 256; ++i) {
-            w[o * 256 + i] = f2bf_bits(proj_w[o * 256 + i]);
-            wt[i * 256 + o] = w[o * 256 + i];
-        }
-    for (int i = 0; i < 256; ++i) mw[i] = f2bf_bits(m_w[i]);
+int gnb_match_init(gnb_ctx* ctx, const float* proj_w, const float* proj_b, const float* m_w, const float* m_b) {
     GNB_CUDA(ctx, cudaMalloc(&ctx->match_w, 256 * 256 * 2));
     GNB_CUDA(ctx, cudaMalloc(&ctx->match_wt, 256 * 256 * 2));
     GNB_CUDA(ctx, cudaMalloc(&ctx->match_b, 256 * 4));
     GNB_CUDA(ctx, cudaMalloc(&ctx->match_mw, 256 * 2));
-    GNB_CUDA(ctx, cudaMemcpy(ctx->match_w, w.data(), 256 * 256 * 2, cudaMemcpyHostToDevice));
-    GNB_CUDA(ctx, cudaMemcpy(ctx->match_wt, wt.data(), 256 * 256 * 2, cudaMemcpyHostToDevice));
-    GNB_CUDA(ctx, cudaMemcpy(ctx->match_b, proj_b, 256 * 4, cudaMemcpyHostToDevice));
-    GNB_CUDA(ctx, cudaMemcpy(ctx->match_mw, mw.data(), 256 * 2, cudaMemcpyHostToDevice));
-    ctx->match_mb = m_b;
+    GNB_KERNEL(ctx, "repack_match_kernel", repack_match_kernel<<<256, 256, 0, ctx->stream>>>(proj_w, m_w, ctx->match_w, ctx->match_wt, ctx->match_mw));
+    GNB_CUDA(ctx, cudaMemcpyAsync(ctx->match_b, proj_b, 256 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    GNB_CUDA(ctx, cudaMemcpyAsync(&ctx->match_mb, m_b, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->cfg.precision == 1) {   // fp32-faithful mode: the head runs in fp32 on the CUDA cores
         GNB_CUDA(ctx, cudaMalloc(&ctx->match_w_f32, 256 * 256 * 4));
         GNB_CUDA(ctx, cudaMalloc(&ctx->match_mw_f32, 256 * 4));
-        GNB_CUDA(ctx, cudaMemcpy(ctx->match_w_f32, proj_w, 256 * 256 * 4, cudaMemcpyHostToDevice));
-        GNB_CUDA(ctx, cudaMemcpy(ctx->match_mw_f32, m_w, 256 * 4, cudaMemcpyHostToDevice));
+        GNB_CUDA(ctx, cudaMemcpyAsync(ctx->match_w_f32, proj_w, 256 * 256 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        GNB_CUDA(ctx, cudaMemcpyAsync(ctx->match_mw_f32, m_w, 256 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    GNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // match_mb is a host field
     return GNB_OK;
 }
 

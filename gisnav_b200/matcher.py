@@ -92,10 +92,38 @@ class KeypointMatcher:
         if not isinstance(desc1, torch.Tensor):
             dists, idx = self.match_arrays(np.asarray(desc1), np.asarray(desc2), centers(lafs1), centers(lafs2), hw1, hw2)
             return torch.from_numpy(dists), torch.from_numpy(idx)
+        if self.ctx.matcher_layers and desc1.is_cuda:
+            # transformer layers loaded: the keypoint centres come from the LAFs, everything stays on the device
+            if lafs1 is None or lafs2 is None:
+                raise ValueError("transformer layers are loaded: the matcher needs lafs (keypoint centres)")
+            d1 = desc1.detach().to(torch.float32).contiguous()
+            d2 = desc2.detach().to(torch.float32).contiguous()
+            k1 = lafs1.detach().to(device=d1.device, dtype=torch.float32).reshape(-1, 2, 3)[:, :, 2].contiguous()
+            k2 = lafs2.detach().to(device=d1.device, dtype=torch.float32).reshape(-1, 2, 3)[:, :, 2].contiguous()
+
+            def hw(kp, given):
+                if given is not None:
+                    return float(given[0]), float(given[1])
+                if kp.shape[0] == 0:
+                    return 1.0, 1.0
+                m = kp.max(dim=0).values.tolist()      # two floats cross PCIe, like kornia's image-size inference
+                return float(m[1]), float(m[0])
+
+            (h1, w1), (h2, w2) = hw(k1, hw1), hw(k2, hw2)
+            n1, n2 = d1.shape[0], d2.shape[0]
+            cap = max(1, min(n1, n2))
+            idx = torch.empty((cap, 2), dtype=torch.int64, device=d1.device)
+            sc = torch.empty((cap,), dtype=torch.float32, device=d1.device)
+            torch.cuda.current_stream(d1.device).synchronize()
+            n = C.c_int(0)
+            self.ctx.check(self.ctx._lib.gnb_match_lightglue(
+                self.ctx.handle, C.c_void_p(d1.data_ptr()), C.c_void_p(k1.data_ptr()), n1, h1, w1, C.c_void_p(d2.data_ptr()),
+                C.c_void_p(k2.data_ptr()), n2, h2, w2, 1, C.c_void_p(idx.data_ptr()), C.c_void_p(sc.data_ptr()), cap, C.byref(n)))
+            return sc[: n.value].reshape(-1, 1), idx[: n.value]
         if self.ctx.matcher_layers:
             dists, idx = self.match_arrays(desc1.detach().cpu().numpy(), desc2.detach().cpu().numpy(), centers(lafs1),
                                            centers(lafs2), hw1, hw2)
-            return torch.from_numpy(dists).to(desc1.device), torch.from_numpy(idx).to(desc1.device)
+            return torch.from_numpy(dists), torch.from_numpy(idx)
         if desc1.is_cuda:
             d1 = desc1.detach().to(torch.float32).contiguous()
             d2 = desc2.detach().to(torch.float32).contiguous()
@@ -134,5 +162,21 @@ class BruteForceRatioMatcher:
         dist = np.empty((cap,), np.float32)
         n = C.c_int(0)
         self.ctx.check(self.ctx._lib.gnb_knn_ratio_match(self.ctx.handle, ptr(dq), dq.shape[0], ptr(dr), dr.shape[0], dim,
-                                                         C.c_float(self.ratio), ptr(idx), ptr(dist), cap, C.byref(n)))
+                                                         C.c_double(self.ratio), 0, ptr(idx), ptr(dist), cap, C.byref(n)))
         return idx[: n.value].copy(), dist[: n.value].copy()
+
+    def knn_ratio_match_device(self, desc_qry, desc_ref):
+        """Same with torch CUDA tensors in and out (no host round trip)."""
+        import torch
+
+        dq = desc_qry.detach().to(torch.float32).contiguous()
+        dr = desc_ref.detach().to(torch.float32).contiguous()
+        cap = max(1, dq.shape[0])
+        idx = torch.empty((cap, 2), dtype=torch.int64, device=dq.device)
+        dist = torch.empty((cap,), dtype=torch.float32, device=dq.device)
+        torch.cuda.current_stream(dq.device).synchronize()
+        n = C.c_int(0)
+        self.ctx.check(self.ctx._lib.gnb_knn_ratio_match(self.ctx.handle, C.c_void_p(dq.data_ptr()), dq.shape[0], C.c_void_p(dr.data_ptr()),
+                                                         dr.shape[0], dq.shape[1], C.c_double(self.ratio), 1, C.c_void_p(idx.data_ptr()),
+                                                         C.c_void_p(dist.data_ptr()), cap, C.byref(n)))
+        return idx[: n.value], dist[: n.value]

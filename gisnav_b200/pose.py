@@ -183,13 +183,42 @@ class PoseEstimator:
         self.ctx.check(self.ctx._lib.gnb_pair_matches(self.ctx.handle, pair, ptr(idx), k, C.byref(n)))
         return idx[: n.value]
 
-    def estimate_from_message(self, query: np.ndarray, reference: np.ndarray, dem: Optional[np.ndarray], camera_info,
-                              crs: str) -> Optional[PoseResult]:
-        """Fields of an ``OrthoStereoImage`` message (ros/gisnav_msgs/msg/OrthoStereoImage.msg:14-18) as
-        PoseNode receives them: mono8 query / reference / dem arrays and the ``+proj=affine`` CRS string."""
+    def estimate_from_records(self, records, reference: np.ndarray, dem: Optional[np.ndarray], camera_info, affine: np.ndarray,
+                              query_hw: Optional[Tuple[int, int]] = None) -> Optional[PoseResult]:
+        """Query side as PRE-EXTRACTED keypoints in the packed wire format (``PointCloud2.data`` of
+        ``OrthoStereoImage.query_sift``: one ``keypoint_dtype(256)`` record per keypoint, 1044 B; _shared.py:26-35,
+        pose_node.py:207-213).  The bytes go to the device as they are and are unpacked there."""
+        from .keypoint_record import keypoint_dtype
+
+        rec = np.frombuffer(records, dtype=np.uint8) if isinstance(records, (bytes, bytearray, memoryview)) else np.ascontiguousarray(records).view(np.uint8).reshape(-1)
+        step = keypoint_dtype(_lib.DESC_DIM).itemsize
+        if rec.size % step:
+            raise ValueError(f"record buffer of {rec.size} bytes is not a multiple of point_step {step}")
+        reference = np.ascontiguousarray(reference, np.uint8)
+        ht, wt = reference.shape
+        if dem is not None:
+            dem = np.ascontiguousarray(dem, np.uint8).reshape(ht, wt)
+        k = _k9(camera_info)
+        a12 = np.ascontiguousarray(np.asarray(affine, np.float64)[:3, :4]).reshape(12)
+        hq, wq = (int(query_hw[0]), int(query_hw[1])) if query_hw is not None else (0, 0)
+        res = _lib.GnbPoseResult()
+        self.ctx.check(self.ctx._lib.gnb_pose_from_records(self.ctx.handle, ptr(rec), rec.size // step, step, _lib.DESC_DIM, hq, wq,
+                                                           ptr(reference), ht, wt, ptr(dem), ptr(k), ptr(a12), C.byref(res)))
+        out = _from_c(res)
+        return out if out.ok else None
+
+    def estimate_from_message(self, query, reference: np.ndarray, dem: Optional[np.ndarray], camera_info, crs: str,
+                              query_hw: Optional[Tuple[int, int]] = None) -> Optional[PoseResult]:
+        """Fields of an ``OrthoStereoImage`` message (ros/gisnav_msgs/msg/OrthoStereoImage.msg:14-18) as PoseNode
+        receives them: mono8 reference / dem arrays, the ``+proj=affine`` CRS string (``_transformations.py:274-327``)
+        and the query either as a mono8 image (2-D uint8 array) or as the ``query_sift`` PointCloud2 payload
+        (bytes / 1-D array of packed 1044-byte keypoint records, pose_node.py:207-213)."""
         from .crs import proj_to_affine
 
-        return self.estimate_from_images(query, reference, dem, camera_info, proj_to_affine(crs))
+        affine = proj_to_affine(crs)
+        if isinstance(query, np.ndarray) and query.ndim == 2 and query.dtype == np.uint8:
+            return self.estimate_from_images(query, reference, dem, camera_info, affine)
+        return self.estimate_from_records(query, reference, dem, camera_info, affine, query_hw)
 
     def estimate_from_images(self, query: np.ndarray, reference: np.ndarray, dem: Optional[np.ndarray], camera_info,
                              affine: np.ndarray) -> Optional[PoseResult]:

@@ -82,8 +82,8 @@ typedef struct gnb_config {
 int gnb_default_config(gnb_config* cfg);
 
 /* Build a context on CUDA device `device`: allocates the workspace, repacks the weight blob
- * (layout: gisnav_b200/weights.py) into per-tap bf16 tiles.  weights may be a host pointer or,
- * after an NCCL broadcast, a device pointer (weights_on_device != 0). */
+ * (layout: gisnav_b200/weights.py) into per-tap bf16 tiles ON THE DEVICE.  weights may be a host pointer
+ * or, after an NCCL broadcast, a device pointer (weights_on_device != 0: consumed in place, no host copy). */
 int gnb_create(const gnb_config* cfg, const void* weights, size_t nbytes, int weights_on_device,
                int device, gnb_ctx** out);
 void gnb_destroy(gnb_ctx* ctx);
@@ -131,11 +131,12 @@ int gnb_match_lightglue(gnb_ctx* ctx, const float* desc_a, const float* kp_a, in
 
 /* TwistNode's visual-odometry matcher — self._bf.knnMatch(desc_qry, desc_ref, k=2) + ratio test
  * `m.distance < 0.7 * n.distance` (ros/gisnav/gisnav/core/twist_node.py:95,248,263-267).  desc f32
- * [n,dim], dim <= 256 (SIFT: 128).  out_idx int64 [cap,2] (queryIdx, trainIdx) in query order,
- * out_dist f32 [cap] = m.distance.  Exact (bit-identical to OpenCV) for integer-valued descriptors
- * 0..255 such as SIFT's; bf16-rounded operands otherwise. */
-int gnb_knn_ratio_match(gnb_ctx* ctx, const float* desc_q, int n_q, const float* desc_r, int n_r, int dim, float ratio,
-                        int64_t* out_idx, float* out_dist, int cap, int* n_out);
+ * [n,dim], dim <= 256 (SIFT: 128); buffers all host or all device (on_device).  out_idx int64 [cap,2]
+ * (queryIdx, trainIdx) in query order, out_dist f32 [cap] = m.distance.  `ratio` is a double and the test
+ * is evaluated in float64 like the Python expression.  Exact (bit-identical to OpenCV) for integer-valued
+ * descriptors 0..255 such as SIFT's; other values are rounded to bf16 (the tensor-core operand type). */
+int gnb_knn_ratio_match(gnb_ctx* ctx, const float* desc_q, int n_q, const float* desc_r, int n_r, int dim, double ratio,
+                        int on_device, int64_t* out_idx, float* out_dist, int cap, int* n_out);
 
 /* compute_pose: mkp_qry f32 [n,2], mkp_ref f32 [n,2], elevation u8 [dem_h,dem_w] (NULL => z=0),
  * k f64 [9] row-major -> r f64 [9] row-major, t f64 [3]; optional inlier mask u8 [n]. */
@@ -167,6 +168,17 @@ typedef struct gnb_pose_result {
 int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, int hq, int wq, const uint8_t* tiles,
                    int ht, int wt, const uint8_t* dems, const double* k9, const double* affine12,
                    int on_device, gnb_pose_result* results);
+
+/* PoseNode._pose as the reference receives its inputs (OrthoStereoImage, ros/gisnav_msgs/msg/OrthoStereoImage.msg:14-18):
+ * the query side is the PointCloud2 `query_sift` payload — n_records packed keypoint records of point_step bytes
+ * (x, y, z, size, angle f32 + descriptor f32[desc_dim]; KEYPOINT_DTYPE, _shared.py:26-35, pose_node.py:207-213) — and
+ * the reference side the mono8 raster + DEM.  records: HOST bytes, copied as they are and unpacked on the device.
+ * desc_dim must be 256 (point_step 1044): the 128-d SIFT layout cannot feed this matcher head.  (hq, wq) = size of the
+ * image the query keypoints came from (used by the transformer layers' position encoding; 0 = raster size).
+ * result: one HOST gnb_pose_result. */
+int gnb_pose_from_records(gnb_ctx* ctx, const void* records, int n_records, int point_step, int desc_dim, int hq, int wq,
+                          const uint8_t* reference, int ht, int wt, const uint8_t* dem, const double* k9,
+                          const double* affine12, gnb_pose_result* result);
 
 /* Candidate search for ONE query frame (BASELINE.json config 4): the frame is extracted once and
  * matched against n_tiles reference rasters (n_tiles <= max_batch).  Raster features are cached on

@@ -712,3 +712,134 @@ def test_candidate_search_with_transformer_layers():
     assert hits3 == 0 and best3 == 1
     np.testing.assert_array_equal(res3[1].r, res0[1].r)
     ctx.close()
+
+
+# ---- wire format and boundary hygiene -----------------------------------------------------
+def test_estimate_from_message_image_and_packed_records():
+    """OrthoStereoImage ingest as PoseNode._pose receives it (OrthoStereoImage.msg:14-18): the CRS arrives as the
+    reference's ``+proj=affine`` string (_transformations.py:274-327); the query either as the mono8 image or as the
+    ``query_sift`` PointCloud2 payload of packed 1044-byte records (pose_node.py:207-213), unpacked on the device."""
+    from gisnav_b200 import crs, keypoint_record
+
+    blob = _trained_blob()
+    ground = synth.ground_texture(1024, seed=21, n_shapes=800)
+    pair = synth.make_pair(ground, 3, frame_hw=(240, 320), tile_size=256, footprint_frac=0.9)
+    ctx = Context(Config(max_batch=2, max_image_h=256, max_image_w=320, max_keypoints=512), weights=blob)
+    pe = PoseEstimator(ctx)
+    want = pe.estimate_from_images(pair.frame, pair.tile, pair.dem, pair.k, pair.affine)
+    assert want is not None
+    # the reference's own string format, e.g. "+proj=affine +xoff=... +s11=..." (proj_to_affine parses it back)
+    s = crs.affine_to_proj(pair.affine)
+    assert s.startswith("+proj=affine")
+    np.testing.assert_allclose(crs.proj_to_affine(s), pair.affine[:3, :4], rtol=0, atol=0)
+    got = pe.estimate_from_message(pair.frame, pair.tile, pair.dem, pair.k, s)
+    assert got is not None and got.n_matches == want.n_matches
+    np.testing.assert_array_equal(got.r, want.r)
+    np.testing.assert_array_equal(got.ecef, want.ecef)
+    # query side as packed keypoint records: same keypoints + descriptors => exactly the same matches and pose
+    xy, _, desc = KeypointExtractor(ctx).detect_and_compute_arrays(pair.frame)
+    payload = keypoint_record.encode(xy, desc)
+    assert len(payload) == len(xy) * 1044
+    rec = pe.estimate_from_message(payload, pair.tile, pair.dem, pair.k, s, query_hw=pair.frame.shape)
+    assert rec is not None and (rec.n_kp_qry, rec.n_matches, rec.n_inliers) == (want.n_kp_qry, want.n_matches, want.n_inliers)
+    np.testing.assert_array_equal(rec.r, want.r)
+    np.testing.assert_array_equal(rec.t, want.t)
+    np.testing.assert_array_equal(rec.ecef, want.ecef)
+    assert pe.estimate_from_message(payload[: 10 * 1044], pair.tile, pair.dem, pair.k, s) is None      # < MIN_MATCHES => None
+    with pytest.raises(ValueError):
+        pe.estimate_from_records(payload[:1000], pair.tile, pair.dem, pair.k, pair.affine)            # not a whole record
+    with pytest.raises(_lib.GnbError):                                                                 # 128-d SIFT records: refused
+        ctx.check(ctx._lib.gnb_pose_from_records(ctx.handle, ptr(np.zeros(532, np.uint8)), 1, 532, 128, 0, 0, ptr(pair.tile), 256, 256, None,
+                                                 ptr(np.ascontiguousarray(pair.k.reshape(9))), ptr(np.ascontiguousarray(pair.affine.reshape(12))),
+                                                 C.byref(_lib.GnbPoseResult())))
+    ctx.close()
+
+
+def test_tile_cache_is_keyed_by_geometry_and_never_serves_failed_entries():
+    blob = _trained_blob()
+    ground = synth.ground_texture(2048, seed=24, n_shapes=3000)
+    ctx = Context(Config(max_batch=2, max_image_h=256, max_image_w=320, max_keypoints=512), weights=blob)
+    pe = PoseEstimator(ctx)
+    p256 = synth.make_pair(ground, 1, frame_hw=(240, 320), tile_size=256)
+    p192 = synth.make_pair(ground, 1, frame_hw=(240, 320), tile_size=192)
+    ids = np.array([7])
+    _, r1, h1 = pe.estimate_candidates(p256.frame, p256.tile[None], ids, None, p256.k, p256.affine[None])
+    _, r2, h2 = pe.estimate_candidates(p256.frame, p256.tile[None], ids, None, p256.k, p256.affine[None])
+    assert (h1, h2) == (0, 1) and r1[0].n_matches == r2[0].n_matches
+    # same id, different raster geometry: must NOT reuse the 256x256 raster's keypoints
+    _, r3, h3 = pe.estimate_candidates(p192.frame, p192.tile[None], ids, None, p192.k, p192.affine[None])
+    assert h3 == 0
+    single = pe.estimate_batch(p192.frame[None], p192.tile[None], None, p192.k[None], p192.affine[None])[0]
+    assert r3[0].n_matches == single.n_matches and r3[0].n_kp_ref == single.n_kp_ref
+    # a call that fails (raster larger than the workspace) leaves no entry behind for its id
+    with pytest.raises(_lib.GnbError):
+        pe.estimate_candidates(p256.frame, np.zeros((1, 512, 512), np.uint8), np.array([99]), None, p256.k, p256.affine[None])
+    _, _, h4 = pe.estimate_candidates(p192.frame, p192.tile[None], np.array([99]), None, p192.k, p192.affine[None])
+    assert h4 == 0
+    ctx.close()
+
+
+def test_twist_matcher_device_tensors(rand_blob):
+    import torch
+
+    from gisnav_b200 import BruteForceRatioMatcher
+    from oracle import bf_ref
+
+    ctx = _ctx(rand_blob, conv_impl=1, match_impl=0, max_keypoints=512)
+    bf = BruteForceRatioMatcher(ctx)
+    rng = np.random.default_rng(8)
+    q = rng.integers(0, 256, (300, 128)).astype(np.float32)
+    r = rng.integers(0, 256, (257, 128)).astype(np.float32)
+    r[:120] = q[:120] + rng.integers(-2, 3, (120, 128))
+    r = np.clip(r, 0, 255).astype(np.float32)
+    idx_ref, dist_ref = bf_ref.knn_ratio_match(q, r)
+    idx, dist = bf.knn_ratio_match_device(torch.from_numpy(q).cuda(), torch.from_numpy(r).cuda())
+    assert idx.is_cuda and idx.dtype == torch.int64
+    np.testing.assert_array_equal(idx.cpu().numpy(), idx_ref)
+    np.testing.assert_array_equal(dist.cpu().numpy(), dist_ref)
+    ctx.close()
+
+
+def test_two_gpus_in_one_process(rand_blob):
+    """Threading model of SURVEY.md §8(b): a context may be used from any host thread, and one process may hold
+    contexts on several GPUs — per-device function attributes and a per-context watchdog word, not process globals."""
+    import threading
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    img = np.ascontiguousarray(synth.ground_texture(512, seed=13, n_shapes=300)[0:96, 0:128])
+    out = {}
+
+    def work(dev):
+        c = Context(Config(max_batch=2, max_image_h=256, max_image_w=320, max_keypoints=128), weights=rand_blob, device=dev)
+        for _ in range(3):
+            out[dev] = KeypointExtractor(c).detect_and_compute_arrays(img)
+        c.close()
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(out[0][0]) > 20
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+
+
+def test_lightglue_matcher_keeps_cuda_tensors_on_the_device(rand_blob):
+    import torch
+
+    n, m, hw = 200, 180, (240, 320)
+    a, kpa, b, kpb = _lg_inputs(n, m, hw, seed=3)
+    ctx = _ctx(rand_blob, max_keypoints=512, match_threshold=0.0)
+    ctx.set_matcher_layers(W.pack_layers(W.layers_random_init(2, seed=5), 2))
+    km = KeypointMatcher(ctx)
+    sc_h, idx_h = km.match_arrays(a, b, kpa, kpb)     # host path, image size inferred from the keypoints
+    lafs = lambda kp: torch.from_numpy(np.concatenate([np.tile(np.eye(2, dtype=np.float32), (len(kp), 1, 1)), kp[:, :, None]], axis=2))[None].cuda()
+    d, i = km(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), lafs(kpa), lafs(kpb))
+    assert d.is_cuda and i.is_cuda and i.dtype == torch.int64
+    np.testing.assert_array_equal(i.cpu().numpy(), idx_h)
+    np.testing.assert_array_equal(d.cpu().numpy(), sc_h)
+    ctx.close()

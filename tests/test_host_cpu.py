@@ -237,7 +237,9 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "matched_frame_pairs_per_sec" and line["unit"] == "pairs/s"
     assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
-    assert line["config"]["workload"].startswith("config 2")
+    assert line["config"]["workload"].startswith("config 3") and line["config"]["config"] == 3
+    assert line["dtype"] == "f32"        # the reference's tensors are fp32 (pose_node.py:254-287): no bf16 emulation on this arm
+    assert "iterationsCount=10" in line["config"]["ransac"] and line["cpu_baseline"]["cv2_ransac_iterations"] == 10
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
