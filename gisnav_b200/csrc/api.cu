@@ -196,6 +196,7 @@ static int alloc_workspace(gnb_ctx* ctx) {
     if (c.precision == 1) {
         rc |= dalloc(ctx, &ctx->mproj_f32, slots * k * 256);
         rc |= dalloc(ctx, &ctx->c_mproj_f32, cc * k * 256);
+        if (c.match_impl == 0) rc |= dalloc(ctx, &ctx->c_mproj_x3, cc * k * 512);
         rc |= dalloc(ctx, &ctx->head_tmp, n * k * 4 + n * k * 4 * 256);
     }
     if (rc) return GNB_E_CUDA;
@@ -227,7 +228,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
                     ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf,
-                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->head_tmp, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
+                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->head_tmp, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
@@ -733,9 +734,10 @@ static void cache_copy(gnb_ctx* ctx, int entry, int slot, bool to_cache) {
         cp(ctx->c_desc + (size_t)entry * k * 256, ctx->desc_f32 + (size_t)slot * k * 256, k * 256 * sizeof(float));
         return;
     }
-    if (ctx->cfg.precision == 1)
+    if (ctx->cfg.precision == 1) {
         cp(ctx->c_mproj_f32 + (size_t)entry * k * 256, ctx->mproj_f32 + (size_t)slot * k * 256, k * 256 * sizeof(float));
-    else
+        if (ctx->mproj_x3) cp(ctx->c_mproj_x3 + (size_t)entry * k * 512, ctx->mproj_x3 + (size_t)slot * k * 512, k * 512 * sizeof(bf16));
+    } else
         cp(ctx->c_mproj + (size_t)entry * k * 256, ctx->mproj + (size_t)slot * k * 256, k * 256 * sizeof(bf16));
     cp(ctx->c_mlogit + (size_t)entry * k, ctx->mlogit + (size_t)slot * k, k * sizeof(float));
 }

@@ -124,7 +124,13 @@ struct gnb_ctx {
     float* match_w_f32;             // fp32-faithful mode: matcher head weights [256 out][256 in] / [256] in fp32
     float* match_mw_f32;
     float* mproj_f32;               // [slots][K][256] fp32 projected descriptors (fp32-faithful mode)
+    bf16* mproj_x3;                 // [slots][K][hi: 256 | lo: 256] their split-bf16 form: operands of the tensor-core matcher
+    float* col_pa;                  // K4 column partials [max_batch][ceil(K/128)][K]: pass 0 max
+    float* col_pb;                  //                                                  pass 0 sum exp
+    float* col_qa;                  //                                                  pass 1 best score
+    float* col_qb;                  //                                                  pass 1 best row (int bits)
     float* c_mproj_f32;             // [cache_cap][K][256] their cached copies
+    bf16* c_mproj_x3;               // [cache_cap][K][512]
     float* head_tmp;                // fp32-faithful mode: [n][cells][65] logits / gathered convDb rows
     // profiling
     int prof_on;
@@ -206,6 +212,7 @@ int gnb_match_tc_init(gnb_ctx* ctx);
 void gnb_tc_state_free(gnb_ctx* ctx);
 int gnb_knn_ratio(gnb_ctx* ctx, const float* dq, int nq, const float* dr, int nr, int dim, double ratio);
 int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass);
+int gnb_match_tc_pairpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a);
 
 // pnp.cu
 int gnb_pnp_pairs(gnb_ctx* ctx, int pairs, int dem_h, int dem_w, int has_dem, int ref_h, int ref_w, int do_tail,

@@ -272,6 +272,18 @@ __global__ void __launch_bounds__(256) mlogit_f32_kernel(const float* __restrict
     if (lane == 0) mlogit[(size_t)slot * k_cap + kp] = fminf(z, 0.f) - log1pf(expf(-fabsf(z)));
 }
 
+// fp32 projected descriptors -> two bf16 terms per value, [row][hi: 256 | lo: 256] (operands of match_pair_tc<.., X3>)
+__global__ void split_rows_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t rows) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 256) return;
+    const size_t r = i >> 8;
+    const int c = (int)(i & 255);
+    const float v = in[i];
+    const bf16 hi = __float2bfloat16_rn(v);
+    out[r * 512 + c] = hi;
+    out[r * 512 + 256 + c] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+}
+
 int gnb_project_f32(gnb_ctx* ctx, int slot0, int n_slots) {
     const int k = ctx->cfg.max_keypoints;
     // rows beyond a slot's keypoint count are projected too (finite garbage-free: the buffers are zero-initialised
@@ -279,6 +291,11 @@ int gnb_project_f32(gnb_ctx* ctx, int slot0, int n_slots) {
     int rc = gnb_gemm256_f32(ctx, 0, ctx->desc_f32 + (size_t)slot0 * k * 256, nullptr, n_slots * k, ctx->match_w_f32, ctx->match_b, 256, 0.25f,
                              ctx->mproj_f32 + (size_t)slot0 * k * 256, 256, "project_f32");
     if (rc) return rc;
+    if (ctx->mproj_x3) {
+        const size_t rows = (size_t)n_slots * k;
+        GNB_KERNEL(ctx, "split_rows_kernel", split_rows_kernel<<<(unsigned)((rows * 256 + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->mproj_f32 + (size_t)slot0 * k * 256, ctx->mproj_x3 + (size_t)slot0 * k * 512, rows));
+    }
     dim3 grid(ceil_div(k * 32, 256), n_slots);
     GNB_KERNEL(ctx, "mlogit_f32_kernel", mlogit_f32_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->desc_f32, ctx->kp_count, slot0, k, ctx->match_mw_f32,
                                                                                    ctx->match_mb, ctx->mlogit));

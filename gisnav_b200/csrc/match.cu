@@ -234,12 +234,15 @@ __global__ void __launch_bounds__(256) match_rows_simt(const T* __restrict__ mpr
 }
 
 // mutual check + threshold + ordered compaction; one CTA per pair.
+// col_pa / col_pb (optional): per-(row block, column) argmax partials of match_pair_tc<1>; the best row of a column is
+// their maximum, ties to the lowest row block (= lowest row index, as within a block)
 __global__ void __launch_bounds__(1024) mutual_kernel(const float* __restrict__ best_val, const int* __restrict__ best_idx,
                                                       const int* __restrict__ kp_count, const float* __restrict__ kp_xy,
                                                       int k_cap, int slot_a0, int stride_a, int slot_b0, int max_pairs, float thr,
                                                       int* __restrict__ match_idx, float* __restrict__ match_score,
                                                       int* __restrict__ match_count, float* __restrict__ mkp_qry,
-                                                      float* __restrict__ mkp_ref) {
+                                                      float* __restrict__ mkp_ref, const float* __restrict__ col_pa,
+                                                      const float* __restrict__ col_pb, int n_rb_cap) {
     __shared__ int warp_sums[32];
     __shared__ int s_base;
     const int pair = blockIdx.x, sa = slot_a0 + pair * stride_a, sb = slot_b0 + pair;
@@ -254,7 +257,21 @@ __global__ void __launch_bounds__(1024) mutual_kernel(const float* __restrict__ 
         float ms = 0.f;
         if (i < na && nb > 0) {
             j = best_idx[(size_t)ra * k_cap + i];
-            if (j >= 0 && best_idx[(size_t)rb * k_cap + j] == i) {
+            int back = -1;
+            if (j >= 0) {
+                if (col_pa) {
+                    float bvv = -INFINITY;
+                    const int n_rb_a = (na + 127) / 128;
+                    for (int b2 = 0; b2 < n_rb_a; ++b2) {
+                        const size_t o = ((size_t)pair * n_rb_cap + b2) * k_cap + j;
+                        const float v = col_pa[o];
+                        if (v > bvv || back < 0) { bvv = v; back = __float_as_int(col_pb[o]); }
+                    }
+                } else {
+                    back = best_idx[(size_t)rb * k_cap + j];
+                }
+            }
+            if (j >= 0 && back == i) {
                 ms = expf(best_val[(size_t)ra * k_cap + i]);
                 ok = ms > thr;
             }
@@ -291,17 +308,19 @@ int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int strid
     const int k = ctx->cfg.max_keypoints;
     const size_t smem = 2 * 256 * 64 * sizeof(float);
     dim3 grid(ceil_div(k, 64), pairs, 2);
-    if (ctx->cfg.precision == 1) {
+    bool partials = false;
+    if (ctx->cfg.match_impl == 0) {
+        // tcgen05: one S per pair and pass (bf16 operands, or split-bf16 x3 in the fp32-faithful mode)
+        int rc;
+        if ((rc = gnb_match_tc_pairpass(ctx, pairs, slot_a0, slot_b0, stride_a))) return rc;
+        partials = true;
+    } else if (ctx->cfg.precision == 1) {
         GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<0, float>, (int)smem));
         GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<1, float>, (int)smem));
         GNB_KERNEL(ctx, "match_rows_f32<0>", match_rows_simt<0, float><<<grid, 256, smem, ctx->stream>>>(ctx->mproj_f32, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
                                                              ctx->row_lse, ctx->best_val, ctx->best_idx));
         GNB_KERNEL(ctx, "match_rows_f32<1>", match_rows_simt<1, float><<<grid, 256, smem, ctx->stream>>>(ctx->mproj_f32, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, mp,
                                                              ctx->row_lse, ctx->best_val, ctx->best_idx));
-    } else if (ctx->cfg.match_impl == 0) {
-        int rc;
-        if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, stride_a, 0))) return rc;
-        if ((rc = gnb_match_tc_rowpass(ctx, pairs, slot_a0, slot_b0, stride_a, 1))) return rc;
     } else {
         GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<0, bf16>, (int)smem));
         GNB_CUDA(ctx, gnb_func_smem(ctx, match_rows_simt<1, bf16>, (int)smem));
@@ -312,7 +331,8 @@ int gnb_match_pairs(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int strid
     }
     GNB_KERNEL(ctx, "mutual_kernel", mutual_kernel<<<pairs, 1024, 0, ctx->stream>>>(ctx->best_val, ctx->best_idx, ctx->kp_count, ctx->kp_xy, k, slot_a0,
                                                    stride_a, slot_b0, mp, ctx->cfg.match_threshold, ctx->match_idx, ctx->match_score,
-                                                   ctx->match_count, ctx->mkp_qry, ctx->mkp_ref));
+                                                   ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, partials ? ctx->col_qa : nullptr,
+                                                   partials ? ctx->col_qb : nullptr, ceil_div(k, 128)));
     return GNB_OK;
 }
 

@@ -277,6 +277,7 @@ struct TcLayerMaps { CUtensorMap w; CUtensorMap w64; CUtensorMap w128; CUtensorM
 struct TcState {
     TcLayerMaps layers[GNB_NUM_LAYERS];
     CUtensorMap match_map;   // mproj [slots][K][256]
+    CUtensorMap match_map_x3;  // mproj_x3 [slots][K][hi 256 | lo 256] (fp32-faithful mode)
     CUtensorMap proj_map;    // match head projection weights [256][256]
     int proj_ready;
 };

@@ -41,8 +41,25 @@ def project(desc: np.ndarray, params: Dict[str, np.ndarray], quantize: bool = Tr
     return _q(m, quantize).numpy(), z.numpy()
 
 
+def _split(x: torch.Tensor):
+    hi = x.to(torch.bfloat16).to(torch.float32)
+    return hi, (x - hi).to(torch.bfloat16).to(torch.float32)
+
+
 @torch.no_grad()
-def assignment_scores(desc_a, desc_b, params, quantize: bool = True) -> np.ndarray:
+def assignment_scores(desc_a, desc_b, params, quantize=True) -> np.ndarray:
+    """``quantize``: True = bf16 operands (fast mode), False = plain fp32, "x3" = the fp32-faithful mode's head:
+    fp32 projection, then S from split-bf16 operands (m = hi + lo; S = hi hi^T + hi lo^T + lo hi^T, fp32 accumulate —
+    three tensor-core MMAs per product)."""
+    if quantize == "x3":
+        ma, za = project(desc_a, params, False)
+        mb, zb = project(desc_b, params, False)
+        ah, al = _split(torch.from_numpy(ma))
+        bh, bl = _split(torch.from_numpy(mb))
+        s = (ah @ bl.t() + al @ bh.t()) + ah @ bh.t()
+        sc = (F.log_softmax(s, 1) + F.log_softmax(s, 0)
+              + F.logsigmoid(torch.from_numpy(za))[:, None] + F.logsigmoid(torch.from_numpy(zb))[None, :])
+        return sc.numpy()
     ma, za = project(desc_a, params, quantize)
     mb, zb = project(desc_b, params, quantize)
     s = torch.from_numpy(ma) @ torch.from_numpy(mb).t()
@@ -53,7 +70,7 @@ def assignment_scores(desc_a, desc_b, params, quantize: bool = True) -> np.ndarr
 
 @torch.no_grad()
 def match(desc_a: np.ndarray, desc_b: np.ndarray, params: Dict[str, np.ndarray],
-          threshold: float = 0.5, quantize: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+          threshold: float = 0.5, quantize=True) -> Tuple[np.ndarray, np.ndarray]:
     """-> (scores f32 [k,1], idx int64 [k,2]) sorted by query index, like the reference call."""
     n, m = desc_a.shape[0], desc_b.shape[0]
     if n == 0 or m == 0:

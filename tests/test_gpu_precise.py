@@ -119,8 +119,11 @@ def test_x3_full_size_parity(weights, hw):
     ctx.close()
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 40), (300, 257, 150), (1, 50, 1), (1024, 1000, 700)])
-def test_x3_matcher_is_the_fp32_head(rand_blob, rand_params, shape):
+@pytest.mark.parametrize("impl", [pytest.param(0, id="tcgen05_x3"), pytest.param(1, id="simt_fp32")])
+@pytest.mark.parametrize("shape", [(64, 64, 40), (300, 257, 150), (1, 50, 1), (1024, 1000, 700), (129, 512, 100)])
+def test_x3_matcher_head(rand_blob, rand_params, shape, impl):
+    """Matcher head of the fp32-faithful mode: fp32 projection, then S on tcgen05 from split-bf16 operands
+    (match_impl = 0: oracle quantize="x3") or entirely in fp32 on the CUDA cores (match_impl = 1: the plain fp32 head)."""
     from oracle import matcher_ref
 
     n, m, shared = shape
@@ -131,11 +134,15 @@ def test_x3_matcher_is_the_fp32_head(rand_blob, rand_params, shape):
     b[perm] = a[:shared] + 0.05 * rng.standard_normal((shared, 256)).astype(np.float32)
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     b /= np.linalg.norm(b, axis=1, keepdims=True)
-    ctx = Context(Config(max_batch=2, max_image_h=64, max_image_w=64, max_keypoints=1024, match_threshold=0.01, precision=1), weights=rand_blob)
+    ctx = Context(Config(max_batch=2, max_image_h=64, max_image_w=64, max_keypoints=1024, match_threshold=0.01, precision=1, match_impl=impl),
+                  weights=rand_blob)
     sc, idx = KeypointMatcher(ctx).match_arrays(a, b)
-    sc_ref, idx_ref = matcher_ref.match(a, b, rand_params, threshold=0.01, quantize=False)
+    sc_ref, idx_ref = matcher_ref.match(a, b, rand_params, threshold=0.01, quantize="x3" if impl == 0 else False)
     np.testing.assert_array_equal(idx, idx_ref)
     np.testing.assert_allclose(sc, sc_ref, rtol=1e-4)
+    sc32, idx32 = matcher_ref.match(a, b, rand_params, threshold=0.01, quantize=False)
+    assert len(idx32) == len(idx) and np.array_equal(idx32, idx)          # and the same matches as the plain fp32 head
+    np.testing.assert_allclose(sc, sc32, rtol=2e-4)
     ctx.close()
 
 

@@ -61,8 +61,8 @@ def main():
         pair = synth.make_pair(ground, s, tuple(args.hw), args.tile)
         ref = run_pair(pair, params, False, args.keypoints, args.iters, match_quant=False)   # fp32 everywhere
         row = {"seed": s}
-        for name, mode in (("bf16", True), ("x3", "x3")):
-            got = run_pair(pair, params, mode, args.keypoints, args.iters, match_quant=(mode is True))
+        for name, mode, mq in (("bf16", True, True), ("x3", "x3", False), ("x3_tc_matcher", "x3", "x3")):
+            got = run_pair(pair, params, mode, args.keypoints, args.iters, match_quant=mq)
             kp_diff = sum(len(a ^ b) // 2 for a, b in zip(ref["kp"], got["kp"]))
             m_common = len(ref["matches"] & got["matches"])
             d = None
@@ -73,7 +73,7 @@ def main():
         rows.append(row)
         print(json.dumps(row), flush=True)
     summary = {"pairs": args.pairs, "seconds": time.time() - t0}
-    for name in ("bf16", "x3"):
+    for name in ("bf16", "x3", "x3_tc_matcher"):
         ds = [r[name]["centre_diff_px"] for r in rows if r[name]["centre_diff_px"] is not None]
         summary[name] = {"median_px": float(np.median(ds)), "max_px": float(np.max(ds)), "rmse_px": float(np.sqrt(np.mean(np.square(ds)))),
                          "frac_le_1e-3": float(np.mean(np.array(ds) <= 1e-3)), "frac_le_1e-2": float(np.mean(np.array(ds) <= 1e-2)),
