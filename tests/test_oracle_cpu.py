@@ -394,3 +394,107 @@ def test_topk_selection_is_unchanged_by_zeroing_below_a_safe_level():
         else:                       # too few: a kernel would lower the level and repeat
             assert sc_full[-1] <= level
     assert len(nms_ref.select_keypoints(np.where(s > np.quantile(s, 0.5), s, 0).astype(np.float32), max_keypoints=-1)[0]) >= k
+
+
+def _published_lightglue_layers(sd, desc0, kp0, hw0, desc1, kp1, hw1, n_layers):
+    """The transformer of the published LightGlue model written against ITS state-dict layout (fused Wqkv with
+    (head, dim, {q,k,v}) interleaving, one to_qk projection shared by both sides of the cross attention, both sides
+    scaled by d^-1/4): an independent statement of what tools/import_lightglue.py must reproduce after renaming."""
+    import torch
+    import torch.nn.functional as F
+
+    def lin(x, name):
+        return x @ sd[name + ".weight"].t() + sd[name + ".bias"]
+
+    def rot_half(x):
+        x = x.unflatten(-1, (-1, 2))
+        x1, x2 = x.unbind(dim=-1)
+        return torch.stack((-x2, x1), dim=-1).flatten(start_dim=-2)
+
+    def posenc(kp, hw):
+        size = torch.tensor([hw[1], hw[0]], dtype=torch.float32)
+        k = (torch.from_numpy(kp) - size / 2) / (size.max() / 2)
+        proj = k @ sd["posenc.Wr.weight"].t()
+        emb = torch.stack([torch.cos(proj), torch.sin(proj)], 0)
+        return emb.repeat_interleave(2, dim=-1)          # [2, n, 64]
+
+    def ffn(x, msg, p):
+        h = lin(torch.cat([x, msg], -1), p + ".ffn.0")
+        h = F.layer_norm(h, (512,), sd[p + ".ffn.1.weight"], sd[p + ".ffn.1.bias"], 1e-5)
+        return x + lin(F.gelu(h), p + ".ffn.3")
+
+    x0, x1 = torch.from_numpy(desc0), torch.from_numpy(desc1)
+    e0, e1 = posenc(kp0, hw0), posenc(kp1, hw1)
+    for i in range(n_layers):
+        p = f"transformers.{i}.self_attn"
+        outs = []
+        for x, e in ((x0, e0), (x1, e1)):
+            qkv = lin(x, p + ".Wqkv").unflatten(-1, (4, -1, 3)).transpose(0, 1)     # [4, n, 64, 3]
+            q, k, v = qkv[..., 0], qkv[..., 1], qkv[..., 2]
+            q = q * e[0] + rot_half(q) * e[1]
+            k = k * e[0] + rot_half(k) * e[1]
+            a = F.softmax(q @ k.transpose(-1, -2) * 64 ** -0.5, -1) @ v
+            outs.append(ffn(x, lin(a.transpose(0, 1).flatten(1), p + ".out_proj"), p))
+        s0, s1 = outs
+        p = f"transformers.{i}.cross_attn"
+        heads = lambda t: t.unflatten(-1, (4, -1)).transpose(0, 1)                  # noqa: E731
+        qk0, qk1 = heads(lin(s0, p + ".to_qk")) * 64 ** -0.25, heads(lin(s1, p + ".to_qk")) * 64 ** -0.25
+        v0, v1 = heads(lin(s0, p + ".to_v")), heads(lin(s1, p + ".to_v"))
+        sim = qk0 @ qk1.transpose(-1, -2)
+        m0 = (F.softmax(sim, -1) @ v1).transpose(0, 1).flatten(1)
+        m1 = (F.softmax(sim.transpose(-1, -2), -1) @ v0).transpose(0, 1).flatten(1)
+        x0, x1 = ffn(s0, lin(m0, p + ".to_out"), p), ffn(s1, lin(m1, p + ".to_out"), p)
+    return x0.numpy(), x1.numpy()
+
+
+def test_import_lightglue_state_dict():
+    """tools/import_lightglue.py on a synthetic state dict in the published layout: the renamed / de-interleaved
+    parameters drive oracle/lightglue_ref.py to the same refined descriptors as the published forward pass."""
+    import importlib.util
+
+    import torch
+
+    from gisnav_b200 import weights as W
+    from oracle import lightglue_ref
+
+    spec = importlib.util.spec_from_file_location("import_lightglue", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "import_lightglue.py"))
+    imp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(imp)
+    g = torch.Generator().manual_seed(3)
+    n_layers = 2
+    sd = {"posenc.Wr.weight": torch.randn(32, 2, generator=g) * 3}
+    for i in range(n_layers):
+        s, c = f"transformers.{i}.self_attn", f"transformers.{i}.cross_attn"
+        shapes = {s + ".Wqkv": (768, 256), s + ".out_proj": (256, 256), c + ".to_qk": (256, 256), c + ".to_v": (256, 256), c + ".to_out": (256, 256)}
+        for blk in (s, c):
+            shapes.update({blk + ".ffn.0": (512, 512), blk + ".ffn.3": (256, 512)})
+        for name, (o, k) in shapes.items():
+            sd[name + ".weight"] = torch.randn(o, k, generator=g) / k ** 0.5
+            sd[name + ".bias"] = torch.randn(o, generator=g) * 0.05
+        for blk in (s, c):
+            sd[blk + ".ffn.1.weight"] = 1 + 0.1 * torch.randn(512, generator=g)
+            sd[blk + ".ffn.1.bias"] = 0.05 * torch.randn(512, generator=g)
+        sd[f"log_assignment.{i}.final_proj.weight"] = torch.randn(256, 256, generator=g) / 16
+        sd[f"log_assignment.{i}.final_proj.bias"] = torch.randn(256, generator=g) * 0.05
+        sd[f"log_assignment.{i}.matchability.weight"] = torch.randn(1, 256, generator=g) / 16
+        sd[f"log_assignment.{i}.matchability.bias"] = torch.randn(1, generator=g)
+    lp, n = imp.convert_layers(sd)
+    assert n == n_layers
+    blob = W.pack_layers(lp, n)                      # shapes match the GNBL layout
+    back, n2 = W.unpack_layers(blob)
+    assert n2 == n and set(back) == set(lp)
+    rng = np.random.default_rng(5)
+    d0 = rng.standard_normal((37, 256)).astype(np.float32); d0 /= np.linalg.norm(d0, axis=1, keepdims=True)
+    d1 = rng.standard_normal((50, 256)).astype(np.float32); d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    hw = (240, 320)
+    k0 = (rng.random((37, 2)) * [320, 240]).astype(np.float32)
+    k1 = (rng.random((50, 2)) * [320, 240]).astype(np.float32)
+    got0, got1 = lightglue_ref.forward(d0, k0, hw, d1, k1, hw, lp, n, emulate_bf16=False)
+    want0, want1 = _published_lightglue_layers(sd, d0, k0, hw, d1, k1, hw, n)
+    np.testing.assert_allclose(got0, want0, rtol=0, atol=2e-4 * np.abs(want0).max())
+    np.testing.assert_allclose(got1, want1, rtol=0, atol=2e-4 * np.abs(want1).max())
+    head = imp.convert_head(sd, n)
+    assert head["match.proj.weight"].shape == (256, 256) and head["match.m.weight"].shape == (256,) and head["match.m.bias"].shape == (1,)
+    np.testing.assert_array_equal(head["match.proj.weight"], sd["log_assignment.1.final_proj.weight"].numpy())
+    with pytest.raises(ValueError):                  # the 128-d 'sift' variant cannot feed this path
+        imp.convert_layers({**sd, "input_proj.weight": torch.zeros(256, 128)})
