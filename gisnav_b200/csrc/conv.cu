@@ -13,6 +13,7 @@
 
 struct CUtensorMap_st;
 const CUtensorMap_st* gnb_conv_tc_wmap(gnb_ctx* ctx, int lid);
+const CUtensorMap_st* gnb_conv_tc_wmap_x3(gnb_ctx* ctx, int lid);
 int gnb_score_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* apa, const float* bias, int n, int hc, int wc, float* score);
 int gnb_conv1_fused_tc(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out_p1);
 int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0);
@@ -307,6 +308,9 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
     int rc;
     if (ctx->cfg.precision == 1) {
         // fp32-faithful mode: conv1a fp32 (CUDA cores) -> split-bf16 tcgen05 stack -> fp32 heads
+        // conv1a stays a separate fp32 kernel in this mode: fusing it into the conv1b kernel (producer warps computing
+        // conv1a into the operand ring) measured SLOWER (36 vs 31 ms per 64 pairs): with hi + lo weights resident only
+        // three 23 KB operand stages fit, so the producers cannot run a tile ahead of the MMA warp
         if ((rc = gnb_conv1a_x3(ctx, cw.img, n, h, w, cw.a1a))) return rc;
         if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
         if ((rc = conv_layer(ctx, L2A, cw.p1, n, h / 2, w / 2, cw.a2a, nullptr, 1, 0))) return rc;
@@ -317,8 +321,8 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
         if ((rc = conv_layer(ctx, L4B, cw.a4a, n, h / 8, w / 8, cw.a4b, nullptr, 1, 0))) return rc;
         if ((rc = conv_layer(ctx, LPA, cw.a4b, n, h / 8, w / 8, cw.apa, nullptr, 1, 0))) return rc;
         const int cells = n * (h / 8) * (w / 8);
-        if ((rc = gnb_gemm256_f32(ctx, 1, cw.apa, nullptr, cells, ctx->layers[LPB].w_f32, ctx->layers[LPB].bias, 65, 1.0f, cw.semi, 65, "score_head_f32"))) return rc;
-        GNB_KERNEL(ctx, "softmax_d2s_kernel", softmax_d2s_kernel<<<ceil_div(cells, 128), 128, 0, ctx->stream>>>(cw.semi, cells, h / 8, w / 8, cw.score));
+        // detector head on tcgen05 with split operands, fused with softmax + depth-to-space (score_head_kernel<X3>)
+        if ((rc = gnb_score_head_tc(ctx, gnb_conv_tc_wmap_x3(ctx, LPB), cw.apa, ctx->layers[LPB].bias, n, h / 8, w / 8, cw.score))) return rc;
         if ((rc = conv_layer(ctx, LDA, cw.a4b, n, h / 8, w / 8, cw.ada, nullptr, 1, 0))) return rc;
         if (dense_desc) {
             if ((rc = gnb_gemm256_f32(ctx, 1, cw.ada, nullptr, cells, ctx->layers[LDB].w_f32, ctx->layers[LDB].bias, 256, 1.0f, cw.dense, 256, "desc_dense_f32"))) return rc;

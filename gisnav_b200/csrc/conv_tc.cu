@@ -1026,6 +1026,10 @@ const CUtensorMap* gnb_conv_tc_wmap(gnb_ctx* ctx, int lid) {
     TcLayerMaps& m = tc_state(ctx)->layers[lid];
     return m.valid ? &m.w : nullptr;
 }
+const CUtensorMap* gnb_conv_tc_wmap_x3(gnb_ctx* ctx, int lid) {   // split (hi | lo) weights of a 1x1 head
+    TcLayerMaps& m = tc_state(ctx)->layers[lid];
+    return m.valid ? &m.x64 : nullptr;
+}
 
 int gnb_conv_tc_init(gnb_ctx* ctx) {
     if (!gnb_tc_err_dev(ctx)) { GNB_SET_ERR(ctx, "cannot allocate the host-mapped error word"); return GNB_E_CUDA; }
@@ -1044,6 +1048,13 @@ int gnb_conv_tc_init(gnb_ctx* ctx) {
         if (L.cout_pad >= 128) {
             const uint32_t box128[3] = {64, 128, 1};
             if ((rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].w128, L.w, 3, dims, strides, box128))) return rc;
+        }
+        if (ctx->cfg.precision == 1 && L.ks == 1) {
+            // 1x1 heads: split weights [1][cout_pad][hi: cin | lo: cin], all output rows in one box
+            const uint64_t xd[3] = {(uint64_t)L.cin * 2, (uint64_t)L.cout_pad, 1};
+            const uint64_t xs[2] = {(uint64_t)L.cin * 4, (uint64_t)L.cout_pad * L.cin * 4};
+            const uint32_t xb[3] = {64, (uint32_t)L.cout_pad, 1};
+            if ((rc = gnb_make_tmap_bf16(ctx, &g_wmaps[l].x64, L.w_x3, 3, xd, xs, xb))) return rc;
         }
         if (ctx->cfg.precision == 1 && L.ks == 3) {
             // split weights [tap][cout_pad][hi: cin | lo: cin]: chunk c of the inner dimension is a hi chunk for

@@ -23,15 +23,22 @@ int* gnb_tc_err_dev(gnb_ctx* ctx);
 #define SH_W_BYTES (4 * SH_NPAD * 128)    // 48 KB
 #define SH_STAGES 2
 #define SH_SMEM (1024 + SH_W_BYTES + SH_STAGES * SH_A_BYTES + 256 + SH_NPAD * 4)
+#define SH_SMEM_X3 (1024 + 2 * SH_W_BYTES + SH_STAGES * SH_A_BYTES + 256 + SH_NPAD * 4)
 
+// X3 (fp32-faithful mode): the activation is [hi: 256 | lo: 256] per cell and the weights [hi | lo] per output row (96 KB
+// resident).  A tile is fed as TWO ring stages — the four hi chunks, then the four lo chunks — and every hi chunk is
+// multiplied with the hi and the lo weight block, every lo chunk with the hi block: three MMAs per product into one
+// accumulator, then the same softmax / depth-to-space epilogue on the fp32 logits.
+template <bool X3>
 __global__ void __launch_bounds__(256, 1) score_head_kernel(const __grid_constant__ CUtensorMap tmap_in,
                                                             const __grid_constant__ CUtensorMap tmap_w,
                                                             const float* __restrict__ bias, int hc, int wc, int n_img,
                                                             float* __restrict__ score, int* err) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int WB = (X3 ? 2 : 1) * SH_W_BYTES, HALVES = X3 ? 2 : 1;
     uint8_t* sW = smem;
-    uint8_t* sA = smem + SH_W_BYTES;
+    uint8_t* sA = smem + WB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + SH_STAGES * SH_A_BYTES);
     uint64_t* w_full = bars;
     uint64_t* a_full = bars + 1;
@@ -62,16 +69,21 @@ __global__ void __launch_bounds__(256, 1) score_head_kernel(const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            tc::mbar_arrive_expect_tx(w_full, SH_W_BYTES);
-            for (int c = 0; c < 4; ++c) tc::tma_load_3d(sW + c * SH_NPAD * 128, &tmap_w, w_full, c * 64, 0, 0);
-            int i = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
-                const int s = i % SH_STAGES;
-                if (i >= SH_STAGES && !tc::mbar_wait(&a_empty[s], ((i / SH_STAGES) & 1) ^ 1, err, 301)) break;
+            tc::mbar_arrive_expect_tx(w_full, WB);
+            for (int c = 0; c < 4 * HALVES; ++c) tc::tma_load_3d(sW + c * SH_NPAD * 128, &tmap_w, w_full, c * 64, 0, 0);
+            int i = 0;   // ring index over (tile, half)
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int y0 = (rem / tiles_x) * 8, x0 = (rem % tiles_x) * 16;
-                tc::mbar_arrive_expect_tx(&a_full[s], SH_A_BYTES);
-                for (int c = 0; c < 4; ++c) tc::tma_load_4d(sA + s * SH_A_BYTES + c * 128 * 128, &tmap_in, &a_full[s], c * 64, x0, y0, img);
+                bool ok = true;
+                for (int hf = 0; hf < HALVES; ++hf, ++i) {
+                    const int s = i % SH_STAGES;
+                    if (i >= SH_STAGES && !tc::mbar_wait(&a_empty[s], ((i / SH_STAGES) & 1) ^ 1, err, 301)) { ok = false; break; }
+                    tc::mbar_arrive_expect_tx(&a_full[s], SH_A_BYTES);
+                    for (int c = 0; c < 4; ++c)
+                        tc::tma_load_4d(sA + s * SH_A_BYTES + c * 128 * 128, &tmap_in, &a_full[s], hf * 256 + c * 64, x0, y0, img);
+                }
+                if (!ok) break;
             }
         }
     } else if (warp == 1) {
@@ -79,25 +91,34 @@ __global__ void __launch_bounds__(256, 1) score_head_kernel(const __grid_constan
         bool ok = tc::mbar_wait(w_full, 0, err, 302);
         const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
         const uint64_t da00 = tc::make_smem_desc_sw128(tc::smem_u32(sA), 1024);
-        int i = 0;
-        for (int tile = blockIdx.x; ok && tile < total; tile += gridDim.x, ++i) {
-            const int s = i % SH_STAGES, as = i & 1;
-            if (!tc::mbar_wait(&a_full[s], (i / SH_STAGES) & 1, err, 303)) break;
-            if (i >= 2 && !tc::mbar_wait(&t_empty[as], ((i >> 1) & 1) ^ 1, err, 304)) break;
-            tc::tc_fence_after();
-            if (tc::elect_one()) {
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
-                const uint64_t da0 = da00 + (uint64_t)((s * SH_A_BYTES) >> 4);
+        int i = 0, ti = 0;
+        for (int tile = blockIdx.x; ok && tile < total; tile += gridDim.x, ++ti) {
+            const int as = ti & 1;
+            if (ti >= 2 && !tc::mbar_wait(&t_empty[as], ((ti >> 1) & 1) ^ 1, err, 304)) break;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+            for (int hf = 0; hf < HALVES; ++hf, ++i) {
+                const int s = i % SH_STAGES;
+                if (!tc::mbar_wait(&a_full[s], (i / SH_STAGES) & 1, err, 303)) { ok = false; break; }
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint64_t da0 = da00 + (uint64_t)((s * SH_A_BYTES) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_bf16(d_tmem, da0 + (uint64_t)((c * 128 * 128 + k * 32) >> 4),
-                                      db0 + (uint64_t)((c * SH_NPAD * 128 + k * 32) >> 4), idesc, (c | k) ? 1u : 0u);
-                tc::umma_commit(&a_empty[s]);
-                tc::umma_commit(&t_full[as]);
+                    for (int term = 0; term < HALVES; ++term) {
+                        if (term < (hf == 0 ? HALVES : 1)) {   // hi half: weight blocks hi (and lo); lo half: weight block hi
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    tc::umma_bf16(d_tmem, da0 + (uint64_t)((c * 128 * 128 + k * 32) >> 4),
+                                                  db0 + (uint64_t)(((term * 4 + c) * SH_NPAD * 128 + k * 32) >> 4), idesc, (hf | term | c | k) ? 1u : 0u);
+                        }
+                    }
+                    tc::umma_commit(&a_empty[s]);
+                    if (hf == HALVES - 1) tc::umma_commit(&t_full[as]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
@@ -156,17 +177,23 @@ __global__ void __launch_bounds__(256, 1) score_head_kernel(const __grid_constan
 
 int gnb_score_head_tc(gnb_ctx* ctx, const CUtensorMap* tmap_w, const bf16* apa, const float* bias, int n, int hc, int wc,
                       float* score) {
+    const bool x3 = ctx->cfg.precision == 1;
+    const uint64_t cin = x3 ? 512 : 256;   // fp32-faithful mode: [hi: 256 | lo: 256] per cell
     CUtensorMap tin;
-    const uint64_t dims[4] = {256, (uint64_t)wc, (uint64_t)hc, (uint64_t)n};
-    const uint64_t strides[3] = {512, (uint64_t)wc * 512, (uint64_t)hc * wc * 512};
+    const uint64_t dims[4] = {cin, (uint64_t)wc, (uint64_t)hc, (uint64_t)n};
+    const uint64_t strides[3] = {cin * 2, (uint64_t)wc * cin * 2, (uint64_t)hc * wc * cin * 2};
     const uint32_t box[4] = {64, 16, 8, 1};
     int rc = gnb_make_tmap_bf16(ctx, &tin, const_cast<bf16*>(apa), 4, dims, strides, box);
     if (rc) return rc;
-    GNB_CUDA(ctx, gnb_func_smem(ctx, score_head_kernel, SH_SMEM));
     const int total = ceil_div(wc, 16) * ceil_div(hc, 8) * n;
     const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-    GNB_KERNEL(ctx, "score_head_tc", score_head_kernel<<<grid, 256, SH_SMEM, ctx->stream>>>(tin, *tmap_w, bias, hc, wc, n, score,
-                                                                                            gnb_tc_err_dev(ctx)));
+    if (x3) {
+        GNB_CUDA(ctx, gnb_func_smem(ctx, score_head_kernel<true>, SH_SMEM_X3));
+        GNB_KERNEL(ctx, "score_head_x3", score_head_kernel<true><<<grid, 256, SH_SMEM_X3, ctx->stream>>>(tin, *tmap_w, bias, hc, wc, n, score, gnb_tc_err_dev(ctx)));
+    } else {
+        GNB_CUDA(ctx, gnb_func_smem(ctx, score_head_kernel<false>, SH_SMEM));
+        GNB_KERNEL(ctx, "score_head_tc", score_head_kernel<false><<<grid, 256, SH_SMEM, ctx->stream>>>(tin, *tmap_w, bias, hc, wc, n, score, gnb_tc_err_dev(ctx)));
+    }
     return GNB_OK;
 }
 
