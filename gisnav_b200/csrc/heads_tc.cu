@@ -362,6 +362,195 @@ int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap* tmap_w, const bf16* ada, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// descriptor head on demand, fp32-faithful mode: the gathered cells are [hi: 256 | lo: 256] (eight 16 KB chunks, all
+// resident), the split weights [256 rows][hi | lo] are STREAMED through a three-stage TMA ring in the order hi0, lo0, hi1,
+// lo1, ... (32 KB per chunk: they do not fit next to the operand), and every weight chunk is multiplied with the
+// activation chunks it pairs with (hi c: A_hi[c] and A_lo[c]; lo c: A_hi[c]) into one fp32 accumulator.  Same epilogue as
+// desc_head_kernel (per-cell L2 norm, bilinear combine, L2 norm) on the fp32 TMEM values.
+#define DX_A_BYTES (8 * 128 * 128)     // 128 KB
+#define DX_W_CHUNK (256 * 128)         // 32 KB
+#define DX_STAGES 3
+#define DX_SMEM (1024 + DX_A_BYTES + DX_STAGES * DX_W_CHUNK + 256 + 256 * 4)
+
+__global__ void __launch_bounds__(256, 1) desc_head_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ ada,
+                                                              const float* __restrict__ bias, int hc, int wc, int img_h, int img_w,
+                                                              const float* __restrict__ kp_xy, const int* __restrict__ kp_count,
+                                                              int slot0, int k_cap, float* __restrict__ desc, int* err) {
+    const int b = blockIdx.y, slot = slot0 + b;
+    const int n_kp = max(kp_count[slot], 0);
+    const int kp0 = blockIdx.x * 32;
+    if (kp0 >= n_kp) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + DX_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + DX_STAGES * DX_W_CHUNK);
+    uint64_t* w_full = bars;                  // [DX_STAGES]
+    uint64_t* w_empty = bars + DX_STAGES;     // [DX_STAGES]
+    uint64_t* acc_full = w_empty + DX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < DX_STAGES; ++s) { tc::mbar_init(&w_full[s], 1); tc::mbar_init(&w_empty[s], 1); }
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) { tc::tmem_alloc(tmem_slot, 256); tc::tmem_relinquish(); }
+    s_bias[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    if (warp == 0 && lane == 0) {   // the first ring stages can stream in while the CTA gathers its operand
+        for (int q = 0; q < DX_STAGES; ++q) {
+            tc::mbar_arrive_expect_tx(&w_full[q], DX_W_CHUNK);
+            tc::tma_load_3d(sW + q * DX_W_CHUNK, &tmap_w, &w_full[q], (q & 1) * 256 + (q >> 1) * 64, 0, 0);
+        }
+    }
+    // ---- gather: row m = 4 * (keypoint - kp0) + corner; 1024 B per row = 8 chunks x 8 sixteen-byte pieces (hi chunks 0-3, lo 4-7)
+    const bf16* base = ada + (size_t)b * hc * wc * 512;
+    for (int item = threadIdx.x; item < 128 * 64; item += 256) {
+        const int m = item >> 6, piece = item & 63;
+        const int kp = kp0 + (m >> 2), corner = m & 3;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (kp < n_kp) {
+            const float x = kp_xy[((size_t)slot * k_cap + kp) * 2 + 0], y = kp_xy[((size_t)slot * k_cap + kp) * 2 + 1];
+            const float gx = __fdiv_rn(__fsub_rn(x, 3.5f), (float)img_w - 4.5f);
+            const float gy = __fdiv_rn(__fsub_rn(y, 3.5f), (float)img_h - 4.5f);
+            const int cx = (int)floorf(__fmul_rn(gx, (float)(wc - 1))) + (corner & 1);
+            const int cy = (int)floorf(__fmul_rn(gy, (float)(hc - 1))) + (corner >> 1);
+            if (cx >= 0 && cx < wc && cy >= 0 && cy < hc)
+                val = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)cy * wc + cx) * 512) + piece);
+        }
+        const int chunk = piece >> 3, j = piece & 7;
+        *reinterpret_cast<uint4*>(sA + chunk * 128 * 128 + m * 128 + ((j ^ (m & 7)) << 4)) = val;
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int q = DX_STAGES; q < 8; ++q) {
+                const int s = q % DX_STAGES;
+                if (!tc::mbar_wait(&w_empty[s], ((q / DX_STAGES) & 1) ^ 1, err, 331)) break;
+                tc::mbar_arrive_expect_tx(&w_full[s], DX_W_CHUNK);
+                tc::tma_load_3d(sW + s * DX_W_CHUNK, &tmap_w, &w_full[s], (q & 1) * 256 + (q >> 1) * 64, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = tc::make_idesc_bf16(128, 256);
+        const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA), 1024);
+        const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int s = q % DX_STAGES;
+            if (ok && !tc::mbar_wait(&w_full[s], (q / DX_STAGES) & 1, err, 332)) ok = false;
+            tc::tc_fence_after();
+            if (ok && tc::elect_one()) {
+                const int c = q >> 1;
+                const uint64_t db = db0 + (uint64_t)((s * DX_W_CHUNK) >> 4);
+#pragma unroll
+                for (int term = 0; term < 2; ++term) {
+                    if (term < ((q & 1) ? 1 : 2)) {   // hi weights: A_hi[c], A_lo[c];  lo weights: A_hi[c]
+                        const uint64_t da = da0 + (uint64_t)(((c + term * 4) * 128 * 128) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (q | term | k) ? 1u : 0u);
+                    }
+                }
+                tc::umma_commit(&w_empty[s]);
+                if (q == 7) tc::umma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                       // TMEM lane = gathered row
+        const int kp = kp0 + (m >> 2), corner = m & 3;
+        float wgt = 0.f;
+        bool valid_cell = false;
+        if (kp < n_kp) {
+            const float x = kp_xy[((size_t)slot * k_cap + kp) * 2 + 0], y = kp_xy[((size_t)slot * k_cap + kp) * 2 + 1];
+            const float gx = __fdiv_rn(__fsub_rn(x, 3.5f), (float)img_w - 4.5f);
+            const float gy = __fdiv_rn(__fsub_rn(y, 3.5f), (float)img_h - 4.5f);
+            const float fx = __fmul_rn(gx, (float)(wc - 1)), fy = __fmul_rn(gy, (float)(hc - 1));
+            const float x0f = floorf(fx), y0f = floorf(fy);
+            const float ax = __fsub_rn(fx, x0f), ay = __fsub_rn(fy, y0f);
+            const int cx = (int)x0f + (corner & 1), cy = (int)y0f + (corner >> 1);
+            valid_cell = cx >= 0 && cx < wc && cy >= 0 && cy < hc;
+            const float wx = (corner & 1) ? ax : 1.f - ax, wy = (corner >> 1) ? ay : 1.f - ay;
+            wgt = __fmul_rn(wx, wy);
+        }
+        const bool ok = tc::mbar_wait(acc_full, 0, err, 333);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (ok) {
+            float ss = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + c0, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float t = __uint_as_float(r[j]) + s_bias[c0 + j]; ss += t * t; }
+            }
+            const float coef = valid_cell ? wgt * (1.0f / fmaxf(sqrtf(ss), 1e-12f)) : 0.f;
+            float so = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + c0, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = (__uint_as_float(r[j]) + s_bias[c0 + j]) * coef;
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    so += t * t;
+                }
+            }
+            const float inv_o = 1.0f / fmaxf(sqrtf(so), 1e-12f);
+            float* o = desc + ((size_t)slot * k_cap + kp) * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + c0, r);
+                tc::tmem_ld_wait();
+                float mine[8];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = (__uint_as_float(r[j]) + s_bias[c0 + j]) * coef;
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    if ((j >> 3) == corner) mine[j & 7] = t * inv_o;
+                }
+                if (kp < n_kp) {
+                    float4* dst = reinterpret_cast<float4*>(o + c0 + corner * 8);
+                    dst[0] = make_float4(mine[0], mine[1], mine[2], mine[3]);
+                    dst[1] = make_float4(mine[4], mine[5], mine[6], mine[7]);
+                }
+            }
+        }
+        tc::tc_fence_before();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 256); }
+}
+
+int gnb_desc_head_x3_tc(gnb_ctx* ctx, const CUtensorMap* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0) {
+    GNB_CUDA(ctx, gnb_func_smem(ctx, desc_head_x3_kernel, DX_SMEM));
+    const int k = ctx->cfg.max_keypoints;
+    dim3 grid(ceil_div(k, 32), n);
+    GNB_KERNEL(ctx, "desc_head_x3", desc_head_x3_kernel<<<grid, 256, DX_SMEM, ctx->stream>>>(
+        *tmap_w, ada, bias, h / 8, w / 8, h, w, ctx->kp_xy, ctx->kp_count, slot0, k, ctx->desc_f32, gnb_tc_err_dev(ctx)));
+    return GNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LightGlue final projection on tcgen05: m = (W d + b) / 256^(1/4) for 128 keypoints per CTA, plus
 // the matchability logit z = w_m . d + b_m as a second, 16-column MMA on the same A operand
 // (B2 = [w_m; 0 ...]).  A = bf16(descriptors) gathered row-wise into the 128B-swizzle layout.

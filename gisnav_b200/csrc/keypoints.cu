@@ -678,8 +678,11 @@ __global__ void __launch_bounds__(NS_THREADS, 3) nms_sparse_kernel(const float* 
     }
 }
 
-// One CTA per image: exact top-K of the candidate keys (radix select on the 64-bit key), then a
-// bitonic sort of the K selected keys in shared memory.
+// One CTA per image: exact top-K of the candidate keys (radix select on the 64-bit key, 8 bits per pass, most
+// significant byte first; the pass loop stops as soon as the selected bin holds exactly the keys still needed, which with
+// distinct scores is after the four score bytes), then a bitonic sort of the selected keys: up to 1024 keys live one per
+// thread and every compare-exchange with a partner less than 32 lanes away is a warp shuffle (40 of the 55 steps), only
+// the wider ones go through shared memory.
 __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __restrict__ cand_keys,
                                                     const int* __restrict__ cand_count, int slot0, int w, int k_cap,
                                                     float* __restrict__ kp_xy, float* __restrict__ kp_score,
@@ -687,7 +690,7 @@ __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __
     __shared__ unsigned long long sel[GNB_MAX_KP];
     __shared__ int hist[256];
     __shared__ unsigned long long s_prefix, s_mask;
-    __shared__ int s_remaining, s_nsel;
+    __shared__ int s_remaining, s_nsel, s_done;
     const int slot = slot0 + blockIdx.x;
     const int n_raw = cand_count[slot];
     if (n_raw > GNB_CAND_CAP) {  // overflow: candidates were dropped in atomic order -> refuse
@@ -695,10 +698,11 @@ __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __
         return;
     }
     const int n = n_raw;
+    const int lane = threadIdx.x & 31;
     const unsigned long long* keys = cand_keys + (size_t)slot * GNB_CAND_CAP;
     unsigned long long kth = ~0ull;
     if (n > k_cap) {
-        if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_remaining = k_cap; }
+        if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_remaining = k_cap; s_done = 0; }
         __syncthreads();
         for (int pass = 7; pass >= 0; --pass) {
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
@@ -709,46 +713,94 @@ __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __
                 if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> (8 * pass)) & 255ull)], 1);
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                int cum = 0, d = 0;
-                for (; d < 255; ++d) {
-                    if (cum + hist[d] >= s_remaining) break;
-                    cum += hist[d];
+            if (threadIdx.x < 32) {
+                // warp 0: lane l owns bins [8 l, 8 l + 8); find the bin where the running count reaches s_remaining
+                int mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mine += hist[lane * 8 + j];
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t2;
                 }
-                s_remaining -= cum;
-                s_prefix |= (unsigned long long)d << (8 * pass);
-                s_mask |= 255ull << (8 * pass);
+                const int before = incl - mine, rem = s_remaining;
+                const bool crossing = before < rem && incl >= rem;   // exactly one lane (the total is >= rem by construction)
+                if (crossing) {
+                    int cum = before, d = lane * 8;
+                    for (; d < lane * 8 + 7; ++d) {
+                        if (cum + hist[d] >= rem) break;
+                        cum += hist[d];
+                    }
+                    s_remaining = rem - cum;
+                    s_prefix = prefix | ((unsigned long long)d << (8 * pass));
+                    s_mask = mask | (255ull << (8 * pass));
+                    // every key of the selected bin is needed: the K-th key is the largest key with this prefix
+                    if (hist[d] == rem - cum) s_done = 1;
+                }
             }
             __syncthreads();
+            if (s_done) break;
         }
-        kth = s_prefix;
+        kth = s_done ? (s_prefix | ~s_mask) : s_prefix;
     }
     if (threadIdx.x == 0) s_nsel = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long key = keys[i];
-        if (key <= kth) {
-            const int pos = atomicAdd(&s_nsel, 1);
-            if (pos < GNB_MAX_KP) sel[pos] = key;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const unsigned long long key = i < n ? keys[i] : ~0ull;
+        const bool take = i < n && key <= kth;
+        const unsigned ballot = __ballot_sync(0xffffffffu, take);
+        if (ballot) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nsel, __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0) + __popc(ballot & ((1u << lane) - 1));
+            if (take && base < GNB_MAX_KP) sel[base] = key;
         }
     }
     __syncthreads();
     const int nsel = min(s_nsel, k_cap);
     int npow = 1;
     while (npow < nsel) npow <<= 1;
-    for (int i = nsel + threadIdx.x; i < npow; i += blockDim.x) sel[i] = ~0ull;
-    __syncthreads();
-    for (int size = 2; size <= npow; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < npow; i += blockDim.x) {
-                const int j = i ^ stride;
-                if (j > i) {
-                    const bool up = (i & size) == 0;
-                    const unsigned long long a = sel[i], c = sel[j];
-                    if ((a > c) == up) { sel[i] = c; sel[j] = a; }
+    if (npow <= 1024) {
+        // one key per thread (threads >= nsel hold the +inf sentinel)
+        unsigned long long key = (int)threadIdx.x < nsel ? sel[threadIdx.x] : ~0ull;
+        const int i = threadIdx.x;
+        for (int size = 2; size <= npow; size <<= 1) {
+            const bool up = (i & size) == 0;
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                unsigned long long other;
+                if (stride >= 32) {
+                    __syncthreads();
+                    sel[i] = key;
+                    __syncthreads();
+                    other = sel[i ^ stride];
+                } else {
+                    other = __shfl_xor_sync(0xffffffffu, key, stride);
                 }
+                const bool lower = (i & stride) == 0;          // this thread keeps the smaller key of the pair when sorting up
+                const bool keep_min = lower == up;
+                key = keep_min ? (other < key ? other : key) : (other > key ? other : key);
             }
-            __syncthreads();
+        }
+        __syncthreads();
+        sel[i] = key;
+        __syncthreads();
+    } else {
+        for (int i = nsel + threadIdx.x; i < npow; i += blockDim.x) sel[i] = ~0ull;
+        __syncthreads();
+        for (int size = 2; size <= npow; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+                    const int j = i ^ stride;
+                    if (j > i) {
+                        const bool up = (i & size) == 0;
+                        const unsigned long long a = sel[i], c = sel[j];
+                        if ((a > c) == up) { sel[i] = c; sel[j] = a; }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     for (int i = threadIdx.x; i < nsel; i += blockDim.x) {

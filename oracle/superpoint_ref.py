@@ -14,9 +14,8 @@ stay fp32.  ``quantize=False`` gives the plain fp32 network for reporting the bf
 conv operand is split into two bf16 terms, ``v = hi + lo`` with ``hi = bf16(v)``, ``lo = bf16(v - hi)``
 (16 significant bits), and the product keeps the three leading terms
 ``a_hi w_hi + a_hi w_lo + a_lo w_hi`` accumulated in fp32 — what three tcgen05 MMAs into one TMEM
-accumulator compute.  Relative error per product ~2^-16 against 2^-8 for plain bf16 operands.  conv1a (Cin = 1)
-and the on-demand descriptor head convDb are plain fp32 in that mode (CUDA cores; convDb reads the activation as
-stored, ``hi + lo``); the detector head convPb uses the split like the 3x3 layers.
+accumulator compute.  Relative error per product ~2^-16 against 2^-8 for plain bf16 operands.  conv1a (Cin = 1) is
+plain fp32 in that mode (CUDA cores); the two 1x1 heads use the split like the 3x3 layers.
 """
 from __future__ import annotations
 
@@ -42,12 +41,8 @@ def _conv(x, p, name, relu=True, quantize=True):
     w = torch.from_numpy(p[name + ".weight"])
     b = torch.from_numpy(p[name + ".bias"])
     pad = w.shape[-1] // 2
-    if quantize == "x3" and name in ("conv1a", "convDb"):
-        # plain fp32 on the CUDA cores: conv1a (Cin = 1) and the on-demand descriptor head, which reads the stored (hi, lo)
-        # activation.  (The detector head convPb runs on the tensor cores with the same split as the 3x3 layers.)
-        if name != "conv1a":
-            xh, xl = split_hi_lo(x)
-            x = xh + xl
+    if quantize == "x3" and name == "conv1a":
+        # Cin = 1, nine FMAs per output: plain fp32 on the CUDA cores
         y = F.conv2d(x, w, b, padding=pad)
     elif quantize == "x3":
         xh, xl = split_hi_lo(x)

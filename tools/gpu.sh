@@ -23,8 +23,17 @@ case "$recipe" in
                python bench.py --steps 2 --warmup 3 --batch 16 --cpu-pairs 0 --acc-pairs 0 --precision $p > gpurun_out/ncu_launches.log 2>&1
              grep -c . gpurun_out/launches_$p.csv ;;
   ncu)       p=${1:-fp32_faithful}; b=${2:-16}
-             # skip the warm-up steps: count the launches of one step from the launch list first (recipe `launches`)
-             skip=${NCU_SKIP:-0}; count=${NCU_COUNT:-80}
+             # one step = the launches between two finalize_kernel launches; take the 4th step (after the warm-up) from the launch list
+             [ -f gpurun_out/launches_$p.csv ] || bash tools/gpu.sh launches $p
+             read skip count < <(python - "$p" <<'PY'
+import csv, sys
+rows = [r for r in csv.reader(open(f"gpurun_out/launches_{sys.argv[1]}.csv")) if len(r) > 5]
+k = rows[0].index("Kernel Name")
+fin = [i for i, r in enumerate(rows[1:]) if "finalize_kernel" in r[k]]
+print(fin[2] + 1, fin[3] - fin[2])
+PY
+)
+             echo "ncu --set full: skip $skip launches, capture $count"
              timeout 1400 ncu --set full --clock-control none --import-source on --launch-skip $skip --launch-count $count -o /tmp/prof_step_$p \
                python bench.py --steps 1 --warmup 3 --batch $b --cpu-pairs 0 --acc-pairs 0 --precision $p > gpurun_out/ncu_step.log 2>&1
              python tools/ncu_summary.py /tmp/prof_step_$p.ncu-rep gpurun_out/ncu_step_$p.json > gpurun_out/ncu_step_$p.md; tail -3 gpurun_out/ncu_step_$p.md ;;
