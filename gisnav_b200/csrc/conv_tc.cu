@@ -193,7 +193,12 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tmap_out, int tstore) {
     constexpr int W_TAP_BYTES = NPAD * 128;        // one (tap, chunk) block
     constexpr int W_BYTES = 9 * KCH * W_TAP_BYTES;
-    constexpr int TMEM_COLS = 2 * NPAD;  // 128 or 256
+    // X3: the hi chunk is multiplied with the hi AND lo weight blocks in ONE MMA of N = 2 NPAD (the two blocks of a tap are
+    // contiguous in shared memory: 8 KB of operands per 64-cycle instruction instead of 2 x 6 KB per 2 x 32 cycles), which
+    // leaves two partial sums per channel — columns [0, NPAD): a_hi w_hi (+ a_lo w_hi from the lo chunk), [NPAD, 2 NPAD):
+    // a_hi w_lo — that the epilogue adds.
+    constexpr int ACC_COLS = X3 ? 2 * NPAD : NPAD;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;  // 128 or 256
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sW = smem;
@@ -261,13 +266,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
         // whole warp stays converged; one elected lane issues.  Descriptors are a 64-bit base plus a
         // compile-time constant per (tap, k-step): one add each.
         const uint32_t idesc = tc::make_idesc_bf16(128, NPAD);
+        const uint32_t idesc2 = tc::make_idesc_bf16(128, X3 ? 2 * NPAD : NPAD);   // X3 hi chunk: N covers the hi and the lo weight block
         bool ok = tc::mbar_wait(w_full, 0, err, 212);
         const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
         int i = 0, ti = 0;
         for (int tile = tile0; ok && tile < total; tile += tstride, ++ti) {
             const int as = ti & 1;
             if (ti >= 2 && !tc::mbar_wait(&t_empty[as], ((ti >> 1) & 1) ^ 1, err, 214)) break;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * NPAD);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
 #pragma unroll
             for (int c = 0; c < KCH; ++c, ++i) {
                 const int s = i % STAGES;
@@ -275,23 +281,18 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
                 tc::tc_fence_after();
                 const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
                 if (tc::elect_one()) {
-                    // X3: hi chunk -> weight blocks {hi, lo} of the same channels; lo chunk -> weight block hi
-                    constexpr int KH = KCH / 2;
-                    const int wc0 = X3 ? (c < KH ? c : c - KH) : c;
-                    const int n_terms = (X3 && c < KH) ? 2 : 1;
+                    // X3 (KCH = 2): chunk 0 = hi activations x [W_hi; W_lo] (one N = 2 NPAD MMA per tap and k-step), chunk 1 = lo
+                    // activations x W_hi (N = NPAD, accumulating into the first NPAD columns)
+                    static_assert(!X3 || KCH == 2, "the split-bf16 single-CTA kernel is written for Cin = 64");
+                    const int wc = X3 ? 0 : c;
+                    const uint32_t id = (X3 && c == 0) ? idesc2 : idesc;
 #pragma unroll
-                    for (int term = 0; term < (X3 ? 2 : 1); ++term) {
-                        if (term < n_terms) {
-                            const int wc = wc0 + term * KH;
+                    for (int t = 0; t < 9; ++t) {
 #pragma unroll
-                            for (int t = 0; t < 9; ++t) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
-                                    const uint64_t db = db0 + (uint64_t)(((t * KCH + wc) * W_TAP_BYTES + k * 32) >> 4);
-                                    tc::umma_bf16(d_tmem, da, db, idesc, (c | term | t | k) ? 1u : 0u);
-                                }
-                            }
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k2 * 32) >> 4);
+                            const uint64_t db = db0 + (uint64_t)(((t * KCH + wc) * W_TAP_BYTES + k2 * 32) >> 4);
+                            tc::umma_bf16(d_tmem, da, db, id, (c | t | k2) ? 1u : 0u);
                         }
                     }
                     tc::umma_commit(&a_empty[s]);
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
             const int y = (rem / tiles_x) * H2_TH + yl, x = (rem % tiles_x) * H2_TW + xl;
             if (!tc::mbar_wait(&t_full[as], (i >> 1) & 1, err, 215)) break;
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * NPAD);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS);
             const bool inside = (y < h) && (x < w);
             size_t pix;
             bool writer;
@@ -326,6 +327,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc_halo_kernel(const __grid_const
             for (int c0 = 0; c0 < NPAD; c0 += 32) {
                 uint32_t v[32];
                 tc::tmem_ld32(taddr + c0, v);
+                if constexpr (X3) {   // add the a_hi w_lo partial sums
+                    uint32_t v2[32];
+                    tc::tmem_ld32(taddr + NPAD + c0, v2);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(v2[j])));
+                }
                 tc::tmem_ld_wait();
                 if constexpr (X3) {
                     uint32_t phi[16], plo[16];
@@ -450,7 +458,12 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
     constexpr int HP_N = NP, HP_NH = NP / 2;
     constexpr int W_TAP_BYTES = HP_NH * 128;
     constexpr int W_BYTES = 9 * KCH * W_TAP_BYTES;
-    constexpr int TMEM_COLS = 2 * HP_N;
+    // X3 (KCH = 4: hi0, hi1, lo0, lo1): a hi chunk is multiplied with its hi AND lo weight rows in ONE pair MMA of
+    // N = 2 NP (each CTA keeps the hi and lo rows of its NP / 2 channels contiguous: blocks are stored hi0, lo0, hi1, lo1),
+    // a lo chunk with the hi rows (N = NP) into a second accumulator region: three partial sums per channel, added by the
+    // epilogue.  Columns of a stage: [0, 2 NP): per CTA half [hh | hl], [2 NP, 3 NP): lh.
+    constexpr int ACC_COLS = X3 ? 4 * HP_N : HP_N;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sW = smem;
@@ -502,7 +515,8 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
             tc::mbar_arrive_expect_tx(w_full, W_BYTES);
             for (int t = 0; t < 9; ++t)
                 for (int c = 0; c < KCH; ++c)
-                    tc::tma_load_3d(sW + (t * KCH + c) * W_TAP_BYTES, &tmap_w, w_full, c * 64, ch0 + (int)rank * HP_NH, t);
+                    tc::tma_load_3d(sW + (t * KCH + (X3 ? (c < KCH / 2 ? 2 * c : 2 * (c - KCH / 2) + 1) : c)) * W_TAP_BYTES, &tmap_w, w_full, c * 64,
+                                    ch0 + (int)rank * HP_NH, t);
             int i = 0;
             for (int tp = tp0; tp < tile_pairs; tp += tpstride) {
                 const int tile = 2 * tp + (int)rank;     // may be == total for the odd tail: the box is then all zero fill
@@ -536,13 +550,14 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
     } else if (warp == 1 && rank == 0) {
         // leader: one elected lane issues the pair-wide MMAs
         const uint32_t idesc = tc::make_idesc_bf16(256, HP_N);
+        const uint32_t idesc2 = tc::make_idesc_bf16(256, X3 ? 2 * HP_N : HP_N);
         bool ok = tc::mbar_wait(w_full, 0, err, 234) && tc::mbar_wait_cluster(pw_full, 0, err, 235);
         const uint64_t db0 = tc::make_smem_desc_sw128(tc::smem_u32(sW), 1024);
         int i = 0, ti = 0;
         for (int tp = tp0; ok && tp < tile_pairs; tp += tpstride, ++ti) {
             const int as = ti & 1;
             if (ti >= 2 && !tc::mbar_wait_cluster(&t_empty[as], ((ti >> 1) & 1) ^ 1, err, 236)) break;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * HP_N);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
 #pragma unroll
             for (int c = 0; c < KCH; ++c, ++i) {
                 const int s = i % STAGES;
@@ -552,21 +567,18 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
                 const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(sA + s * H2_HALO_STRIDE), H2_HW * 128);
                 if (tc::elect_one()) {
                     constexpr int KH = KCH / 2;
-                    const int wc0 = X3 ? (c < KH ? c : c - KH) : c;
-                    const int n_terms = (X3 && c < KH) ? 2 : 1;
+                    const bool lo_chunk = X3 && c >= KH;
+                    const int wpos = X3 ? 2 * (lo_chunk ? c - KH : c) : c;            // weight block: its hi rows (X3: followed by its lo rows)
+                    const uint32_t id = (X3 && !lo_chunk) ? idesc2 : idesc;
+                    const uint32_t d_out = d_tmem + (lo_chunk ? (uint32_t)(2 * HP_N) : 0u);
+                    const int first = lo_chunk ? c - KH : c;                           // first chunk writing this accumulator region
 #pragma unroll
-                    for (int term = 0; term < (X3 ? 2 : 1); ++term) {
-                        if (term < n_terms) {
-                            const int wc = wc0 + term * KH;
+                    for (int t = 0; t < 9; ++t) {
 #pragma unroll
-                            for (int t = 0; t < 9; ++t) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k * 32) >> 4);
-                                    const uint64_t db = db0 + (uint64_t)(((t * KCH + wc) * W_TAP_BYTES + k * 32) >> 4);
-                                    tc::umma_bf16_pair(d_tmem, da, db, idesc, (c | term | t | k) ? 1u : 0u);
-                                }
-                            }
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            const uint64_t da = da0 + (uint64_t)((((t / 3) * H2_HW + (t % 3)) * 128 + k2 * 32) >> 4);
+                            const uint64_t db = db0 + (uint64_t)(((t * KCH + wpos) * W_TAP_BYTES + k2 * 32) >> 4);
+                            tc::umma_bf16_pair(d_out, da, db, id, (first | t | k2) ? 1u : 0u);
                         }
                     }
                     tc::umma_commit_pair(&a_empty[s]);
@@ -589,7 +601,7 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
             const int y = (rem / tiles_x) * H2_TH + yl, x = (rem % tiles_x) * H2_TW + xl;
             if (!tc::mbar_wait_cluster(&t_full[as], (i >> 1) & 1, err, 239)) break;
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * HP_N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS);
             const bool inside = (tile < total) && (y < h) && (x < w);
             size_t pix;
             bool writer;
@@ -603,8 +615,20 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gr
 #pragma unroll 1
             for (int c0 = 0; c0 < HP_N; c0 += 32) {
                 uint32_t v[32];
-                tc::tmem_ld32(taddr + c0, v);
-                tc::tmem_ld_wait();
+                if constexpr (X3) {
+                    // channels [c0, c0 + 32) belong to CTA (c0 / 32)'s weight rows: hh at 64 r, hl at 64 r + 32, lh at 2 NP + c0
+                    uint32_t v2[32], v3[32];
+                    tc::tmem_ld32(taddr + 2 * c0, v);
+                    tc::tmem_ld32(taddr + 2 * c0 + 32, v2);
+                    tc::tmem_ld32(taddr + 2 * HP_N + c0, v3);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = __float_as_uint(__fadd_rn(__fadd_rn(__uint_as_float(v2[j]), __uint_as_float(v3[j])), __uint_as_float(v[j])));
+                } else {
+                    tc::tmem_ld32(taddr + c0, v);
+                    tc::tmem_ld_wait();
+                }
                 if constexpr (X3) {
                     uint32_t phi[16], plo[16];
                     tc::epilogue_split32(v, &s_bias[c0], relu, pool, phi, plo);

@@ -16,8 +16,8 @@
 // conv1a, fp32: same tiling as conv1a_kernel (conv.cu).  Output pixel = 128 bf16: hi[64] then lo[64].
 #define X1_TH 8
 #define X1_TW 32
-__global__ void __launch_bounds__(256) conv1a_x3_kernel(const uint8_t* __restrict__ img, const float* __restrict__ wt,
-                                                        const float* __restrict__ bias, int h, int w, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(256, 4) conv1a_x3_kernel(const uint8_t* __restrict__ img, const float* __restrict__ wt,
+                                                           const float* __restrict__ bias, int h, int w, bf16* __restrict__ out) {
     __shared__ float patch[X1_TH + 2][X1_TW + 2 + 2];
     const int b = blockIdx.z, y0 = blockIdx.y * X1_TH, x0 = blockIdx.x * X1_TW;
     const uint8_t* im = img + (size_t)b * h * w;
@@ -28,39 +28,41 @@ __global__ void __launch_bounds__(256) conv1a_x3_kernel(const uint8_t* __restric
         if (y >= 0 && y < h && x >= 0 && x < w) f = __fdiv_rn((float)im[(size_t)y * w + x], 255.0f);
         patch[ly][lx] = f;
     }
+    // lane l owns channels [4 (l % 16), +4) of pixel (l / 16) of a 2-pixel group: its 36 weights live in registers (four
+    // CTAs per SM), and the 16 lanes of a pixel write its 128-byte hi block and its 128-byte lo block with one 8-byte store each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = (lane & 7) * 8, sub = lane >> 3;
-    float wr[9][8], br[8];
+    const int c0 = (lane & 15) * 4, sub = lane >> 4;
+    float wr[9][4], br[4];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wr[t][j] = wt[t * 64 + c0 + j];   // w_f32 [tap][cout_pad = 64][cin = 1]
+        for (int j = 0; j < 4; ++j) wr[t][j] = wt[t * 64 + c0 + j];   // w_f32 [tap][cout_pad = 64][cin = 1]
 #pragma unroll
-    for (int j = 0; j < 8; ++j) br[j] = bias[c0 + j];
+    for (int j = 0; j < 4; ++j) br[j] = bias[c0 + j];
     __syncthreads();
     const int ly = warp, y = y0 + ly;
     if (y >= h) return;
-#pragma unroll 2
-    for (int it = 0; it < X1_TW / 4; ++it) {
-        const int lx = it * 4 + sub, x = x0 + lx;
+#pragma unroll 4
+    for (int it = 0; it < X1_TW / 2; ++it) {
+        const int lx = it * 2 + sub, x = x0 + lx;
         float v[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) v[t] = patch[ly + t / 3][lx + t % 3];
-        __align__(16) __nv_bfloat162 rh[4], rl[4];
+        float a[4];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) { a0 = fmaf(v[t], wr[t][j], a0); a1 = fmaf(v[t], wr[t][j + 1], a1); }
-            a0 = fmaxf(a0 + br[j], 0.f); a1 = fmaxf(a1 + br[j + 1], 0.f);
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(a0, a1);
-            rh[j / 2] = hi;
-            rl[j / 2] = __floats2bfloat162_rn(__fsub_rn(a0, __low2float(hi)), __fsub_rn(a1, __high2float(hi)));
+            for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wr[t][j], acc);
+            a[j] = fmaxf(acc + br[j], 0.f);
         }
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(__fsub_rn(a[0], __low2float(h0)), __fsub_rn(a[1], __high2float(h0)));
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(__fsub_rn(a[2], __low2float(h1)), __fsub_rn(a[3], __high2float(h1)));
         if (x < w) {
             bf16* o = out + ((size_t)b * h * w + (size_t)y * w + x) * 128 + c0;
-            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(rh);
-            *reinterpret_cast<uint4*>(o + 64) = *reinterpret_cast<const uint4*>(rl);
+            *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            *reinterpret_cast<uint2*>(o + 64) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
         }
     }
 }
