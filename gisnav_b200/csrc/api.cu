@@ -197,7 +197,6 @@ static int alloc_workspace(gnb_ctx* ctx) {
         rc |= dalloc(ctx, &ctx->mproj_f32, slots * k * 256);
         rc |= dalloc(ctx, &ctx->c_mproj_f32, cc * k * 256);
         if (c.match_impl == 0) rc |= dalloc(ctx, &ctx->c_mproj_x3, cc * k * 512);
-        rc |= dalloc(ctx, &ctx->head_tmp, n * k * 4 + n * k * 4 * 256);
     }
     if (rc) return GNB_E_CUDA;
     if (c.precision == 1) GNB_CUDA(ctx, cudaMemset(ctx->mproj_f32, 0, slots * k * 256 * sizeof(float)));
@@ -228,7 +227,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
                     ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf,
-                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->head_tmp, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
+                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);

@@ -131,7 +131,6 @@ struct gnb_ctx {
     float* col_qb;                  //                                                  pass 1 best row (int bits)
     float* c_mproj_f32;             // [cache_cap][K][256] their cached copies
     bf16* c_mproj_x3;               // [cache_cap][K][512]
-    float* head_tmp;                // fp32-faithful mode: [n][cells][65] logits / gathered convDb rows
     // profiling
     int prof_on;
     void* prof;  // ProfState*

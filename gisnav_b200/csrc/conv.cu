@@ -21,7 +21,6 @@ int gnb_desc_head_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* ada
 int gnb_conv1a_x3(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out);
 int gnb_gemm256_f32(gnb_ctx* ctx, int amode, const void* a, const int* row_idx, int m_rows, const float* wgt, const float* bias, int n_cols,
                     float scale, float* c, int ldc, const char* name);
-int gnb_describe_x3(gnb_ctx* ctx, int n, int h, int w, int slot0);
 int gnb_desc_head_x3_tc(gnb_ctx* ctx, const CUtensorMap_st* tmap_w, const bf16* ada, const float* bias, int n, int h, int w, int slot0);
 
 struct LayerSpec { const char* name; int cin, cout, ks; };
@@ -368,10 +367,8 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
 }
 
 int gnb_describe(gnb_ctx* ctx, int n, int h, int w, int slot0) {
-    static const int f32_desc = getenv("GNB_X3_F32_DESC") ? atoi(getenv("GNB_X3_F32_DESC")) : 0;
-    if (ctx->cfg.precision == 1 && !f32_desc)   // on demand, tcgen05 with split operands
+    if (ctx->cfg.precision == 1)   // on demand, tcgen05 with split operands
         return gnb_desc_head_x3_tc(ctx, gnb_conv_tc_wmap_x3(ctx, LDB), ctx->cw.ada, ctx->layers[LDB].bias, n, h, w, slot0);
-    if (ctx->cfg.precision == 1) return gnb_describe_x3(ctx, n, h, w, slot0);   // fp32 CUDA-core GEMM (A/B switch)
     if (ctx->cfg.conv_impl == 0)
         return gnb_desc_head_tc(ctx, gnb_conv_tc_wmap(ctx, LDB), ctx->cw.ada, ctx->layers[LDB].bias, n, h, w, slot0);
     return gnb_kp_sample(ctx, ctx->cw.dense, n, h, w, slot0);

@@ -6,8 +6,8 @@
 // channel blocks [hi: C | lo: C]; the 3x3 layers with Cin >= 64 run on tcgen05 with three MMAs per product
 // (conv_tc.cu, X3 kernels).  What is left runs here in plain fp32 on the CUDA cores because it is < 1 % of the FLOPs:
 //   conv1a        (Cin = 1: nine FMAs per output, write-bound)          u8 image -> [hi|lo] x 64 channels
-//   convPb/convDb (1x1 heads, K = 256) as ONE generic SIMT GEMM         rows = cells (dense) or gathered cells (on demand)
-//   descriptor combine (per-cell L2 norm, bilinear, L2 norm)            oracle/sample_ref.py
+//   the matcher head's projection and the dense descriptor map of the parity hook as a generic SIMT GEMM (K = 256)
+// (the two 1x1 heads of the product path run on tcgen05 with the same split: heads_tc.cu)
 #include "common.cuh"
 
 #include <math.h>
@@ -161,85 +161,6 @@ int gnb_gemm256_f32(gnb_ctx* ctx, int amode, const void* a, const int* row_idx, 
         GNB_KERNEL(ctx, name, gemm256_f32_kernel<0><<<grid, 256, 0, ctx->stream>>>(a, row_idx, m_rows, wgt, bias, n_cols, scale, c, ldc));
     else
         GNB_KERNEL(ctx, name, gemm256_f32_kernel<1><<<grid, 256, 0, ctx->stream>>>(a, row_idx, m_rows, wgt, bias, n_cols, scale, c, ldc));
-    return GNB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// On-demand descriptor head, fp32: (1) which four coarse cells does each keypoint touch, (2) convDb at those
-// cells through gemm256_f32_kernel, (3) per-cell L2 norm, bilinear combine, L2 norm (oracle/sample_ref.py).
-__global__ void __launch_bounds__(256) desc_cells_kernel(const float* __restrict__ kp_xy, const int* __restrict__ kp_count, int slot0,
-                                                         int k_cap, int hc, int wc, int img_h, int img_w, int* __restrict__ row_idx) {
-    const int b = blockIdx.y, slot = slot0 + b;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (keypoint, corner)
-    if (i >= k_cap * 4) return;
-    const int kp = i >> 2, corner = i & 3;
-    int idx = -1;
-    if (kp < kp_count[slot]) {
-        const float x = kp_xy[((size_t)slot * k_cap + kp) * 2 + 0], y = kp_xy[((size_t)slot * k_cap + kp) * 2 + 1];
-        const float gx = __fdiv_rn(__fsub_rn(x, 3.5f), (float)img_w - 4.5f);
-        const float gy = __fdiv_rn(__fsub_rn(y, 3.5f), (float)img_h - 4.5f);
-        const int cx = (int)floorf(__fmul_rn(gx, (float)(wc - 1))) + (corner & 1);
-        const int cy = (int)floorf(__fmul_rn(gy, (float)(hc - 1))) + (corner >> 1);
-        if (cx >= 0 && cx < wc && cy >= 0 && cy < hc) idx = (b * hc + cy) * wc + cx;
-    }
-    row_idx[(size_t)b * k_cap * 4 + i] = idx;
-}
-
-// one warp per keypoint; lane l owns channels [8l, 8l + 8).  rows: [n][k_cap][4][256] raw convDb outputs (+ bias).
-__global__ void __launch_bounds__(256) desc_combine_kernel(const float* __restrict__ rows, const int* __restrict__ row_idx,
-                                                           const float* __restrict__ kp_xy, const int* __restrict__ kp_count, int slot0,
-                                                           int k_cap, int hc, int wc, int img_h, int img_w, float* __restrict__ desc) {
-    const int b = blockIdx.y, slot = slot0 + b;
-    const int kp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (kp >= kp_count[slot]) return;
-    const float x = kp_xy[((size_t)slot * k_cap + kp) * 2 + 0], y = kp_xy[((size_t)slot * k_cap + kp) * 2 + 1];
-    const float gx = __fdiv_rn(__fsub_rn(x, 3.5f), (float)img_w - 4.5f);
-    const float gy = __fdiv_rn(__fsub_rn(y, 3.5f), (float)img_h - 4.5f);
-    const float fx = __fmul_rn(gx, (float)(wc - 1)), fy = __fmul_rn(gy, (float)(hc - 1));
-    const float ax = __fsub_rn(fx, floorf(fx)), ay = __fsub_rn(fy, floorf(fy));
-    const float wq[4] = {__fmul_rn(1.f - ax, 1.f - ay), __fmul_rn(ax, 1.f - ay), __fmul_rn(1.f - ax, ay), __fmul_rn(ax, ay)};
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    const size_t base = ((size_t)b * k_cap + kp) * 4;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (row_idx[base + c] < 0) continue;   // outside the map: zeros (grid_sample padding)
-        const float4* p = reinterpret_cast<const float4*>(rows + (base + c) * 256 + lane * 8);
-        const float4 a = p[0], d = p[1];
-        const float t[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss = fmaf(t[j], t[j], ss);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize of the cell's descriptor
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(v[j], __fmul_rn(__fmul_rn(t[j], inv), wq[c]));
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-    float4* o = reinterpret_cast<float4*>(desc + ((size_t)slot * k_cap + kp) * 256 + lane * 8);
-    o[0] = make_float4(v[0] / nrm, v[1] / nrm, v[2] / nrm, v[3] / nrm);
-    o[1] = make_float4(v[4] / nrm, v[5] / nrm, v[6] / nrm, v[7] / nrm);
-}
-
-int gnb_describe_x3(gnb_ctx* ctx, int n, int h, int w, int slot0) {
-    const int k = ctx->cfg.max_keypoints, hc = h / 8, wc = w / 8;
-    int* row_idx = reinterpret_cast<int*>(ctx->head_tmp);                          // [n][k][4]
-    float* rows = ctx->head_tmp + (size_t)ctx->cfg.max_batch * k * 4;              // [n][k][4][256]
-    dim3 g1(ceil_div(k * 4, 256), n);
-    GNB_KERNEL(ctx, "desc_cells_kernel", desc_cells_kernel<<<g1, 256, 0, ctx->stream>>>(ctx->kp_xy, ctx->kp_count, slot0, k, hc, wc, h, w, row_idx));
-    int rc = gnb_gemm256_f32(ctx, 1, ctx->cw.ada, row_idx, n * k * 4, ctx->layers[LDB].w_f32, ctx->layers[LDB].bias, 256, 1.0f, rows, 256,
-                             "desc_head_f32");
-    if (rc) return rc;
-    dim3 g2(ceil_div(k * 32, 256), n);
-    GNB_KERNEL(ctx, "desc_combine_kernel", desc_combine_kernel<<<g2, 256, 0, ctx->stream>>>(rows, row_idx, ctx->kp_xy, ctx->kp_count, slot0, k, hc, wc, h, w,
-                                                                                       ctx->desc_f32));
     return GNB_OK;
 }
 

@@ -121,207 +121,6 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
 }
 
 // ------------------------------------------------------------------------------------------------
-// NMS specialised for radius 4 (the SuperPoint default): 64x64 output tile + 20 px halo = 104x104
-// region in shared memory.
-//   * the three score max-pools are separable 9-wide filters; a work item owns a run of R consecutive
-//     outputs of one row/column, loads its R+8 inputs once and forms the maxima by doubling
-//     (m2 -> m4 -> m8 -> m9): 5 max ops per output.  Each pool only covers the region the later
-//     stages still need (96^2, 80^2, 64^2 outputs), and "suppressed -> 0" is applied on the fly from
-//     the suppression bit mask instead of materialising supp_scores;
-//   * the two mask max-pools are dilations: done on 128-bit row bitmasks with shifts and ORs;
-//   * adjacent lanes own adjacent lines => row pass strides by the (odd) pitch, column pass is
-//     contiguous: no bank conflicts.
-// Compare-only arithmetic, same decisions as simple_nms => bit-identical survivors.
-#define N4_TILE 64
-#define N4_REG 104
-#define N4_PITCH 105
-#define N4_THREADS 416
-#define N4_WORDS 4   // 104 columns -> 4 x 32-bit mask words per row
-
-// one separable pass; outputs [out_lo, out_lo + 8*R) along the run direction for lines [line_lo, line_lo + n_lines)
-template <bool ROWS, int R, typename Src, typename Sink>
-__device__ __forceinline__ void n4_pass(int line_lo, int n_lines, int out_lo, Src src, Sink sink) {
-    const float NEG = -INFINITY;
-    for (int item = threadIdx.x; item < n_lines * 8; item += N4_THREADS) {
-        const int line = line_lo + item % n_lines, run = item / n_lines;
-        const int o0 = out_lo + run * R, p0 = o0 - 4;
-        float v[R + 8];
-        src(line, p0, v);   // v[k] = input at position p0 + k along the run (NEG outside the region)
-        float m2[R + 7], m4[R + 5], m8[R + 1];
-#pragma unroll
-        for (int k = 0; k < R + 7; ++k) m2[k] = fmaxf(v[k], v[k + 1]);
-#pragma unroll
-        for (int k = 0; k < R + 5; ++k) m4[k] = fmaxf(m2[k], m2[k + 2]);
-#pragma unroll
-        for (int k = 0; k < R + 1; ++k) m8[k] = fmaxf(m4[k], m4[k + 4]);
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const float m9 = fmaxf(m8[k], v[k + 8]);
-            if (ROWS) sink(line, o0 + k, m9); else sink(o0 + k, line, m9);
-        }
-    }
-    (void)NEG;
-}
-
-// 9x9 dilation of the bit mask `in` into `out` (rows of 4 words); `tmp` holds the horizontal pass
-__device__ __forceinline__ void n4_dilate(const unsigned* __restrict__ in, unsigned* __restrict__ tmp, unsigned* __restrict__ out) {
-    for (int y = threadIdx.x; y < N4_REG; y += N4_THREADS) {
-        unsigned r[4], a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = in[y * N4_WORDS + i];
-        auto shl = [](const unsigned x[4], int s, unsigned o[4]) {   // towards higher column index
-            o[0] = x[0] << s;
-#pragma unroll
-            for (int i = 1; i < 4; ++i) o[i] = (x[i] << s) | (x[i - 1] >> (32 - s));
-        };
-        shl(r, 1, a);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= r[i];            // offsets 0..1
-        shl(a, 2, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= b[i];            // 0..3
-        shl(a, 4, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= b[i];            // 0..7
-        shl(r, 8, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] |= b[i];            // 0..8
-        // centre: shift right by 4 (towards lower column index)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tmp[y * N4_WORDS + i] = (a[i] >> 4) | (i < 3 ? (a[i + 1] << 28) : 0u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < N4_REG * N4_WORDS; i += N4_THREADS) {
-        const int y = i / N4_WORDS, wdx = i % N4_WORDS;
-        const int lo = max(y - 4, 0), hi = min(y + 4, N4_REG - 1);
-        unsigned acc = 0;
-        for (int yy = lo; yy <= hi; ++yy) acc |= tmp[yy * N4_WORDS + wdx];
-        out[i] = acc;
-    }
-}
-
-__global__ void __launch_bounds__(N4_THREADS, 2) nms_r4_kernel(const float* __restrict__ score, int h, int w, float threshold,
-                                                               int border, int slot0, unsigned long long* __restrict__ cand_keys,
-                                                               int* __restrict__ cand_count) {
-    extern __shared__ float sm[];
-    float* S = sm;                                   // scores, -inf outside the image
-    float* T = S + N4_REG * N4_PITCH;                // row-pass result
-    unsigned* M = reinterpret_cast<unsigned*>(T + N4_REG * N4_PITCH);   // max_mask bits
-    unsigned* P = M + N4_REG * N4_WORDS;             // supp_mask bits
-    unsigned* H = P + N4_REG * N4_WORDS;             // dilation temp
-    const int b = blockIdx.z;
-    const int y0 = blockIdx.y * N4_TILE - NMS_HALO, x0 = blockIdx.x * N4_TILE - NMS_HALO;
-    const float* sc = score + (size_t)b * h * w;
-    const float NEG = -INFINITY;
-    for (int i = threadIdx.x; i < N4_REG * N4_REG; i += N4_THREADS) {
-        const int ly = i / N4_REG, lx = i - ly * N4_REG;
-        const int y = y0 + ly, x = x0 + lx;
-        S[ly * N4_PITCH + lx] = (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(&sc[(size_t)y * w + x]) : NEG;
-    }
-    for (int i = threadIdx.x; i < N4_REG * N4_WORDS; i += N4_THREADS) M[i] = 0u;
-    __syncthreads();
-
-    auto in_range = [](int p) { return p >= 0 && p < N4_REG; };
-    // sources: plain scores / scores with suppressed pixels set to 0 / row-pass result along columns
-    auto srcS_row = [&](int y, int p0, float* v) {
-#pragma unroll
-        for (int k = 0; k < 20; ++k) v[k] = in_range(p0 + k) ? S[y * N4_PITCH + p0 + k] : NEG;
-    };
-    auto setM = [&](int y, int x) { atomicOr(&M[y * N4_WORDS + (x >> 5)], 1u << (x & 31)); };
-    auto getP = [&](int y, int x) { return (P[y * N4_WORDS + (x >> 5)] >> (x & 31)) & 1u; };
-
-    // pool 1 on raw scores: outputs [4,100)^2, runs of 12
-    n4_pass<true, 12>(0, N4_REG, 4, srcS_row, [&](int y, int x, float m) { T[y * N4_PITCH + x] = m; });
-    __syncthreads();
-    n4_pass<false, 12>(4, 96, 4,
-        [&](int x, int p0, float* v) {
-#pragma unroll
-            for (int k = 0; k < 20; ++k) v[k] = in_range(p0 + k) ? T[(p0 + k) * N4_PITCH + x] : NEG;
-        },
-        [&](int y, int x, float m) {
-            const float s = S[y * N4_PITCH + x];
-            if (s != NEG && s == m) setM(y, x);
-        });
-    __syncthreads();
-
-    // iteration 1: supp valid on [8,96)^2, pooled suppressed scores on [12,92)^2 (runs of 10)
-    n4_dilate(M, H, P);
-    __syncthreads();
-    n4_pass<true, 10>(8, 88, 12,
-        [&](int y, int p0, float* v) {
-#pragma unroll
-            for (int k = 0; k < 18; ++k) {
-                const int x = p0 + k;
-                const float s = S[y * N4_PITCH + x];
-                v[k] = (s != NEG && getP(y, x)) ? 0.f : s;
-            }
-        },
-        [&](int y, int x, float m) { T[y * N4_PITCH + x] = m; });
-    __syncthreads();
-    n4_pass<false, 10>(12, 80, 12,
-        [&](int x, int p0, float* v) {
-#pragma unroll
-            for (int k = 0; k < 18; ++k) v[k] = T[(p0 + k) * N4_PITCH + x];
-        },
-        [&](int y, int x, float m) {
-            const float s = S[y * N4_PITCH + x];
-            if (s != NEG && s == m && !getP(y, x)) setM(y, x);   // new_max & ~supp  (supp_score == score when !supp)
-        });
-    __syncthreads();
-
-    // iteration 2: supp valid on [16,88)^2, pooled on [20,84)^2 = the output tile (runs of 8)
-    n4_dilate(M, H, P);
-    __syncthreads();
-    n4_pass<true, 8>(16, 72, 20,
-        [&](int y, int p0, float* v) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int x = p0 + k;
-                const float s = S[y * N4_PITCH + x];
-                v[k] = (s != NEG && getP(y, x)) ? 0.f : s;
-            }
-        },
-        [&](int y, int x, float m) { T[y * N4_PITCH + x] = m; });
-    __syncthreads();
-    n4_pass<false, 8>(20, 64, 20,
-        [&](int x, int p0, float* v) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = T[(p0 + k) * N4_PITCH + x];
-        },
-        [&](int y, int x, float m) {
-            const float s = S[y * N4_PITCH + x];
-            if (s != NEG && s == m && !getP(y, x)) setM(y, x);
-        });
-    __syncthreads();
-
-    for (int i = threadIdx.x; i < N4_TILE * N4_TILE; i += N4_THREADS) {
-        const int ly = i / N4_TILE + NMS_HALO, lx = i % N4_TILE + NMS_HALO;
-        const int y = y0 + ly, x = x0 + lx;
-        bool keep = false;
-        float s = 0.f;
-        if (y < h && x < w) {
-            s = S[ly * N4_PITCH + lx];
-            keep = ((M[ly * N4_WORDS + (lx >> 5)] >> (lx & 31)) & 1u) && s > threshold && y >= border && y < h - border &&
-                   x >= border && x < w - border;
-        }
-        const unsigned ballot = __ballot_sync(__activemask(), keep);
-        if (keep) {
-            const int lane = threadIdx.x & 31;
-            const int leader = __ffs(ballot) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&cand_count[slot0 + b], __popc(ballot));
-            base = __shfl_sync(ballot, base, leader);
-            const int pos = base + __popc(ballot & ((1u << lane) - 1));
-            if (pos < GNB_CAND_CAP) {
-                const unsigned long long key =
-                    ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(s)) << 32) | (unsigned)(y * w + x);
-                cand_keys[(size_t)(slot0 + b) * GNB_CAND_CAP + pos] = key;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Sparse, top-K-aware NMS (radius 4) — the product path.
 //
 // Lemma (tests/test_oracle_cpu.py::test_nms_survivors_above_a_level_depend_only_on_pixels_above_it): for any level T
@@ -725,6 +524,7 @@ __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __
                     if (lane >= o) incl += t2;
                 }
                 const int before = incl - mine, rem = s_remaining;
+                __syncwarp();   // every lane has read s_remaining before the crossing lane rewrites it
                 const bool crossing = before < rem && incl >= rem;   // exactly one lane (the total is >= rem by construction)
                 if (crossing) {
                     int cum = before, d = lane * 8;
@@ -820,7 +620,7 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         return GNB_E_INVALID;
     }
     GNB_CUDA(ctx, cudaMemsetAsync(ctx->cand_count + slot0, 0, sizeof(int) * n, ctx->stream));
-    static const int dense_nms = getenv("GNB_NMS_DENSE") ? atoi(getenv("GNB_NMS_DENSE")) : 0;
+    static const int dense_nms = getenv("GNB_NMS_DENSE") ? atoi(getenv("GNB_NMS_DENSE")) : 0;   // A/B: the dense generic-radius kernel
     if (ctx->cfg.nms_radius == 4 && ctx->cfg.keypoint_threshold >= 0.f && !dense_nms) {
         // sparse, top-K-aware path (see above)
         const int k_cap = ctx->cfg.max_keypoints;
@@ -844,12 +644,6 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
                                                                                                ctx->nms_flag));
         GNB_KERNEL(ctx, "nms_sparse_kernel(redo)", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
             score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 1, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
-    } else if (ctx->cfg.nms_radius == 4) {
-        const size_t smem = (size_t)N4_REG * N4_PITCH * 2 * sizeof(float) + 3 * N4_REG * N4_WORDS * sizeof(unsigned);
-        GNB_CUDA(ctx, gnb_func_smem(ctx, nms_r4_kernel, (int)smem));
-        dim3 grid(ceil_div(w, N4_TILE), ceil_div(h, N4_TILE), n);
-        GNB_KERNEL(ctx, "nms_r4_kernel", nms_r4_kernel<<<grid, N4_THREADS, smem, ctx->stream>>>(
-            score, h, w, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->cand_keys, ctx->cand_count));
     } else {
         const size_t smem = (size_t)NMS_REG * NMS_REG * (4 * sizeof(float) + 2);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_kernel, (int)smem));

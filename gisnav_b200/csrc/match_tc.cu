@@ -85,11 +85,13 @@ int gnb_tc_err_check(gnb_ctx* ctx) {
     return GNB_OK;
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(MT_THREADS, 1) match_rows_tc(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mlogit,
+// Row pass for the TwistNode matcher: brute-force L2 2-NN of every row of side A against side B (d^2 = |a|^2 + |b|^2 - 2 a.b),
+// the two smallest distances per row (lowest index on ties).  (The LightGlue head uses match_pair_tc below.)
+__global__ void __launch_bounds__(MT_THREADS, 1) match_knn_tc(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ mlogit,
                                                         const int* __restrict__ kp_count, int k_cap, int slot_a0, int stride_a, int slot_b0, int max_pairs,
                                                         float* __restrict__ row_lse, float* __restrict__ best_val,
                                                         int* __restrict__ best_idx, int* err) {
+    constexpr int PASS = 2;
     const int pair = blockIdx.y, side = blockIdx.z;
     const int slot_a = slot_a0 + pair * stride_a, slot_b = slot_b0 + pair;
     const int slot_r = side == 0 ? slot_a : slot_b, slot_c = side == 0 ? slot_b : slot_a;
@@ -575,9 +577,7 @@ int gnb_match_tc_init(gnb_ctx* ctx) {
     const uint32_t box[3] = {MT_KC, 128, 1};
     int rc = gnb_make_tmap_bf16(ctx, g_tmap_host, ctx->mproj, 3, dims, strides, box);
     if (rc) return rc;
-    GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
-    GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
-    GNB_CUDA(ctx, cudaFuncSetAttribute(match_rows_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
+    GNB_CUDA(ctx, cudaFuncSetAttribute(match_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
     GNB_CUDA(ctx, cudaFuncSetAttribute(match_pair_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mp_smem_bytes<false>()));
     GNB_CUDA(ctx, cudaFuncSetAttribute(match_pair_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mp_smem_bytes<false>()));
     const size_t n_rb = (size_t)ceil_div((int)k, 128);
@@ -598,18 +598,13 @@ int gnb_match_tc_init(gnb_ctx* ctx) {
     return GNB_OK;
 }
 
+// brute-force 2-NN row pass (gnb_knn_ratio)
 int gnb_match_tc_rowpass(gnb_ctx* ctx, int pairs, int slot_a0, int slot_b0, int stride_a, int pass) {
+    if (pass != 2) { GNB_SET_ERR(ctx, "gnb_match_tc_rowpass: only the kNN pass is a row pass"); return GNB_E_INVALID; }
     const int k = ctx->cfg.max_keypoints;
     CUtensorMap* g_tmap_host = &tc_state(ctx)->match_map;
-    dim3 grid(ceil_div(k, MT_BM), pairs, pass == 2 ? 1 : 2);
-    if (pass == 2)
-        GNB_KERNEL(ctx, "match_rows_tc<2>", match_rows_tc<2><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, gnb_tc_err_dev(ctx)));
-    else if (pass == 0)
-        GNB_KERNEL(ctx, "match_rows_tc<0>", match_rows_tc<0><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, gnb_tc_err_dev(ctx)));
-    else
-        GNB_KERNEL(ctx, "match_rows_tc<1>", match_rows_tc<1><<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
-            *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, gnb_tc_err_dev(ctx)));
+    dim3 grid(ceil_div(k, MT_BM), pairs, 1);
+    GNB_KERNEL(ctx, "match_knn_tc", match_knn_tc<<<grid, MT_THREADS, MT_SMEM_BYTES, ctx->stream>>>(
+        *g_tmap_host, ctx->mlogit, ctx->kp_count, k, slot_a0, stride_a, slot_b0, ctx->cfg.max_batch, ctx->row_lse, ctx->best_val, ctx->best_idx, gnb_tc_err_dev(ctx)));
     return GNB_OK;
 }
