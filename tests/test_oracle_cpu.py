@@ -498,3 +498,40 @@ def test_import_lightglue_state_dict():
     np.testing.assert_array_equal(head["match.proj.weight"], sd["log_assignment.1.final_proj.weight"].numpy())
     with pytest.raises(ValueError):                  # the 128-d 'sift' variant cannot feed this path
         imp.convert_layers({**sd, "input_proj.weight": torch.zeros(256, 128)})
+
+
+def test_split_bf16_contract_sits_between_bf16_and_fp32():
+    """The three arithmetic contracts of the oracle on one small image: the split-bf16 ("x3") network must agree with the
+    plain fp32 network ~2^8 times better than the bf16 network does (that factor is the whole point of the
+    fp32-faithful mode), select the same keypoints, and its matcher head must reproduce the fp32 head's matches."""
+    from gisnav_b200 import weights as W
+
+    params = W.unpack(W.pack(W.random_init(0)))
+    img = np.ascontiguousarray(synth.ground_texture(512, seed=11, n_shapes=300)[40:136, 60:188])
+    s32, d32 = superpoint_ref.forward_dense(img, params, quantize=False)
+    s16, d16 = superpoint_ref.forward_dense(img, params, quantize=True)
+    sx3, dx3 = superpoint_ref.forward_dense(img, params, quantize="x3")
+    e16, ex3 = np.abs(s16 - s32).max() / s32.max(), np.abs(sx3 - s32).max() / s32.max()
+    assert ex3 < 2e-4 and e16 > 20 * ex3, (e16, ex3)
+    assert np.abs(dx3 - d32).max() < 5e-5 and np.abs(d16 - d32).max() > 20 * np.abs(dx3 - d32).max()
+    # keypoint SETS (seeded-random weights give a flat score map whose near-ties may swap in order): x3 keeps >= 98 of the
+    # fp32 network's 100, the bf16 network visibly fewer or as many
+    k32, _ = nms_ref.select_keypoints(s32, max_keypoints=100)
+    kx3, _ = nms_ref.select_keypoints(sx3, max_keypoints=100)
+    k16, _ = nms_ref.select_keypoints(s16, max_keypoints=100)
+    common = lambda p, q: len(set(map(tuple, p.tolist())) & set(map(tuple, q.tolist())))  # noqa: E731
+    assert common(k32, kx3) >= 98 and common(k32, kx3) >= common(k32, k16)
+    # split (hi, lo) really is a 16-bit representation
+    x = torch.randn(1000) * 3
+    hi, lo = superpoint_ref.split_hi_lo(x)
+    assert float(((hi + lo) - x).abs().max() / x.abs().max()) < 2.0 ** -16
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((120, 256)).astype(np.float32); a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b = np.concatenate([a[:80] + 0.05 * rng.standard_normal((80, 256)).astype(np.float32), rng.standard_normal((30, 256)).astype(np.float32)])
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    s_f, i_f = matcher_ref.match(a, b, params, threshold=0.01, quantize=False)
+    s_x, i_x = matcher_ref.match(a, b, params, threshold=0.01, quantize="x3")
+    s_b, i_b = matcher_ref.match(a, b, params, threshold=0.01, quantize=True)
+    np.testing.assert_array_equal(i_f, i_x)
+    np.testing.assert_allclose(s_x, s_f, rtol=2e-4)
+    assert len(i_b) > 0.9 * len(i_f)
