@@ -610,12 +610,13 @@ def run_b200(args):
         dom = next((r for r in hrep["roofline_per_kernel"] if r["kernel"] == dom_name), None) or \
             max((r for r in hrep["roofline_per_kernel"] if r.get("frac")), key=lambda r: r["ms_per_step"])
         launches_dom = dom.get("launches_per_step", 2) or 2
-        traffic = None
+        traffic = tensor_pipe = None
         try:  # dram bytes per launch from the committed `ncu --set full` capture of this kernel, scaled to this batch
             cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dominant.json")))
             row = cap.get(dom["kernel"])
             if row:
                 traffic = (row["dram_read_bytes"] + row["dram_write_bytes"]) * (px_step / launches_dom) / row["pixels_per_launch"]
+                tensor_pipe = row.get("tensor_pipe_active_pct")
         except (OSError, ValueError, KeyError):
             pass
         in_b = 256 if head["precision"] == 1 else 1
@@ -625,6 +626,7 @@ def run_b200(args):
                                                                else "conv1_fused_kernel: im2col -> tcgen05 conv1a -> TMEM -> tcgen05 conv1b -> pool") + ")",
             "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"],
             "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/r02_ncu_dominant.json)",
+            "tensor_pipe_active_pct_ncu": tensor_pipe,   # sm__pipe_tensor_cycles_active from the same capture: the clock-independent utilisation
             "algorithmic_flop_per_launch": dom["work_per_step"] * 1e12 / launches_dom,
             "algorithmic_bytes_per_launch": px_step / launches_dom * (in_b + out_b),
             "peak_source": peak_src + (" / 3: three MMAs per algorithmic product in the fp32-faithful mode" if head["precision"] == 1 else ""),

@@ -190,3 +190,36 @@ def test_x3_end_to_end_vs_the_fp32_network():
     assert d.max() <= 0.5, rows
     assert sum(sum(r["kp_differ"]) for r in rows) <= 2 * n_pairs, rows
     ctx.close()
+
+
+def test_x3_composes_with_layers_and_candidate_cache():
+    """fp32-faithful mode through the other entry points: residual-zero transformer layers leave the poses unchanged,
+    and the candidate search (tile-feature cache holding fp32 + split projected descriptors) reproduces the batch path
+    on a cold and on a fully cached call."""
+    if not os.path.exists(W.DEFAULT_WEIGHTS_PATH):
+        pytest.skip("trained weights not present")
+    blob = W.load()
+    ground = synth.ground_texture(2048, seed=24, n_shapes=3000)
+    pairs = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256) for s in (1, 2)]
+    ctx = Context(Config(max_batch=4, max_image_h=256, max_image_w=320, max_keypoints=512, precision=1), weights=blob)
+    pe = PoseEstimator(ctx)
+    args = (np.stack([p.frame for p in pairs]), np.stack([p.tile for p in pairs]), None, np.stack([p.k for p in pairs]),
+            np.stack([p.affine for p in pairs]))
+    base = pe.estimate_batch(*args)
+    assert all(r.ok for r in base)
+    decoys = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256).tile for s in (11, 12)]
+    tiles = np.stack([decoys[0], pairs[0].tile, decoys[1]])
+    ids = np.array([100, 101, 102])
+    affs = np.stack([pairs[0].affine] * 3)
+    for expect_hits in (0, 3):
+        best, res, hits = pe.estimate_candidates(pairs[0].frame, tiles, ids, None, pairs[0].k, affs)
+        assert hits == expect_hits and best == 1
+        assert (res[1].n_matches, res[1].n_inliers) == (base[0].n_matches, base[0].n_inliers)
+        np.testing.assert_array_equal(res[1].r, base[0].r)
+        np.testing.assert_array_equal(res[1].ecef, base[0].ecef)
+    ctx.set_matcher_layers(W.pack_layers(W.layers_random_init(2, seed=1, residual_zero=True), 2))
+    with_layers = pe.estimate_batch(*args)
+    for a, b in zip(base, with_layers):
+        assert b.ok and a.n_matches == b.n_matches
+        np.testing.assert_array_equal(a.r, b.r)
+    ctx.close()
