@@ -244,3 +244,31 @@ def test_bench_reference_arm_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["value"] > 0 and line["matched_fraction"] == 1.0
+
+
+def test_bench_roofline_table_and_config_contract():
+    """bench.py host logic without a GPU: every BASELINE config is defined with the keys the JSON line needs, and the
+    per-kernel roofline table maps event-profile rows to their algorithmic work and governing roof."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert sorted(bench.CONFIGS) == [1, 2, 3, 4, 5]
+    assert bench.CONFIGS[3]["batch"] == 64 and bench.CONFIGS[5]["batch"] == 512 and bench.CONFIGS[5]["keypoints"] == 2048
+    assert bench.CONFIGS[5]["scaling"] == "strong" and bench.CONFIGS[3]["scaling"] == "weak" and bench.CONFIGS[2]["batch"] == 1
+    assert abs(bench.FLOP_PER_PIXEL - 169608.0) < 1e-6      # SURVEY.md §8(d): 84 804 MAC per input pixel
+    px = 64 * (720 * 1280 + 1024 * 1024)
+    prof = {"conv_x3:1b": (100.0, 10), "nms_sparse_kernel": (5.0, 10), "match_pair_x3<0>": (1.0, 5), "match_pair_x3<1>": (1.5, 5),
+            "match_collse_kernel": (0.05, 5), "topk_kernel": (0.5, 10), "some_future_kernel": (0.1, 5)}
+    rows = bench.kernel_rooflines(prof, 5, px, 128, 64, 1024, 2048, True, {"bf16_tflops_sustained": 1200.0, "hbm_gbs": 6000.0})
+    by = {r["kernel"]: r for r in rows}
+    c1b = by["conv_x3:1b"]
+    assert c1b["bound"] == "tensor" and abs(c1b["peak"] - 400.0) < 1e-9                      # three MMAs per product: peak / 3
+    assert abs(c1b["work_per_step"] - 2 * 36864 * px / 1e12) < 1e-9 and abs(c1b["frac"] - c1b["achieved"] / 400.0) < 1e-12
+    assert by["nms_sparse_kernel"]["bound"] == "hbm" and abs(by["nms_sparse_kernel"]["work_per_step"] - 4 * px / 1e9) < 1e-9
+    m = by["matcher S = m_a m_b^T (all passes)"]
+    assert abs(m["ms_per_step"] - (1.0 + 1.5 + 0.05) / 5) < 1e-9 and abs(m["work_per_step"] - 2 * 64 * 1024 * 1024 * 256 / 1e12) < 1e-12
+    assert by["topk_kernel"]["bound"] == "latency" and by["some_future_kernel"]["bound"] == "latency"
+    cfg = bench.workload_config(type("A", (), {"config": 5, "matcher_layers": 0})(), bench.CONFIGS[5])
+    assert cfg["pairs_per_step_total"] == 512 and cfg["pairs_per_step_per_gpu"] is None and "iterationsCount=10" in cfg["ransac"]
