@@ -146,7 +146,6 @@ static int alloc_workspace(gnb_ctx* ctx) {
     cw.img = cw.img_a;
     const size_t pf = c.precision == 1 ? 2 : 1;   // fp32-faithful mode: every activation is a (hi, lo) pair of bf16
     rc |= dalloc(ctx, &cw.a1a, n * px * 64 * pf);
-    if (c.precision == 1) rc |= dalloc(ctx, &ctx->a1a_side, n * px * 64 * pf);
     rc |= dalloc(ctx, &cw.p1, n * px / 4 * 64 * pf);
     rc |= dalloc(ctx, &cw.a2a, n * px / 4 * 64 * pf);
     rc |= dalloc(ctx, &cw.p2, n * px / 16 * 64 * pf);
@@ -230,7 +229,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
                     ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf,
-                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->a1a_side, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
+                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
@@ -246,8 +245,6 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
     if (ctx->ev_frames) cudaEventDestroy(ctx->ev_frames);
     if (ctx->ev_tiles) cudaEventDestroy(ctx->ev_tiles);
     if (ctx->ev_params) cudaEventDestroy(ctx->ev_params);
-    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
-    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -294,8 +291,6 @@ extern "C" int gnb_create(const gnb_config* cfg, const void* weights, size_t nby
     if (cudaSetDevice(device) != cudaSuccess) { GNB_SET_ERR(ctx, "cudaSetDevice failed"); return fail(GNB_E_CUDA); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_frames, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_tiles, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_params, cudaEventDisableTiming) != cudaSuccess) {
@@ -584,7 +579,6 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
     if (rc < 0) {
         // an error path must not leave copies of the caller's buffers in flight: the caller may free or reuse them
         cudaStreamSynchronize(ctx->copy_stream);
-        cudaStreamSynchronize(ctx->side_stream);
         cudaStreamSynchronize(ctx->stream);
     }
     return rc;
@@ -609,16 +603,6 @@ static int pose_batch_impl(gnb_ctx* ctx, int batch, const uint8_t* frames, int h
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->affine, affine12, sizeof(double) * 12 * batch, kin, cs));
     if (dems) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dems, (size_t)batch * ht * wt, kin, cs));
     GNB_CUDA(ctx, cudaEventRecord(ctx->ev_params, cs));
-    // fp32-faithful mode: the rasters' conv1a (an HBM write stream) starts now on the side stream, as one thin CTA per
-    // SM that co-resides with the tensor-bound kernels of the frame pass below (not while per-kernel profiling is on:
-    // the profile wants every kernel alone on the main stream)
-    static const int use_side = getenv("GNB_SIDE_STREAM") ? atoi(getenv("GNB_SIDE_STREAM")) : 0;   // off until measured (tools/gpu.sh)
-    const bool side = ctx->cfg.precision == 1 && !ctx->prof_on && use_side;
-    if (side) {
-        GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_tiles, 0));
-        if ((rc = gnb_conv1a_x3_side(ctx, ctx->side_stream, cw.img_b, batch, ht, wt, ctx->a1a_side))) return rc;
-        GNB_CUDA(ctx, cudaEventRecord(ctx->ev_side, ctx->side_stream));
-    }
     // query frames -> slots [0, batch)
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_frames, 0));
     cw.img = cw.img_a;
@@ -636,8 +620,7 @@ static int pose_batch_impl(gnb_ctx* ctx, int batch, const uint8_t* frames, int h
     {
         GnbRange r1("K1 dense stack (rasters)");
         cw.img = cw.img_b;
-        if (side) GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-        rc = gnb_conv_forward(ctx, batch, ht, wt, 0, side ? ctx->a1a_side : nullptr);
+        rc = gnb_conv_forward(ctx, batch, ht, wt, 0);
         cw.img = cw.img_a;
         if (rc) return rc;
     }

@@ -54,9 +54,6 @@ struct gnb_ctx {
     cudaStream_t stream;
     cudaStream_t copy_stream;           // H2D staging of the batch path, overlapped with compute
     cudaEvent_t ev_frames, ev_tiles, ev_params;
-    cudaStream_t side_stream;           // fp32-faithful mode: the rasters' conv1a runs here, under the frames' tensor-core kernels
-    cudaEvent_t ev_side;
-    bf16* a1a_side;                     // [n][h][w][128] its output (second conv1a buffer)
     char err[512];
     int64_t launches;
     ConvLayer layers[GNB_NUM_LAYERS];
@@ -191,8 +188,7 @@ static inline cudaError_t gnb_func_smem(gnb_ctx* ctx, F* func, int bytes) { retu
 int gnb_conv_init(gnb_ctx* ctx, const float* blob_floats_dev);  // repack weights (device pointer to the blob's floats)
 void gnb_conv_free(gnb_ctx* ctx);
 // run the dense stack on cw.img (n images of h x w already resident)
-int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc, const bf16* a1a_ready = nullptr);
-int gnb_conv1a_x3_side(gnb_ctx* ctx, cudaStream_t stream, const uint8_t* img, int n, int h, int w, bf16* out);   // conv_x3.cu
+int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc);
 // descriptors of the selected keypoints of `n` images (slots slot0..): on-demand tcgen05 head or dense+sample
 int gnb_describe(gnb_ctx* ctx, int n, int h, int w, int slot0);
 // tcgen05 implicit-GEMM conv (conv_tc.cu); returns GNB_E_INVALID if a layer shape is unsupported

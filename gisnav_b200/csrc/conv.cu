@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) l2norm256_kernel(float* __restrict__ d, i
 }
 
 // ------------------------------------------------------------------------------------------------
-int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc, const bf16* a1a_ready) {
+int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc) {
     ConvWorkspace& cw = ctx->cw;
     if (n > cw.cap_images || (size_t)h * w > cw.cap_pixels || (h % 8) || (w % 8)) {
         GNB_SET_ERR(ctx, "conv_forward: %d images of %dx%d exceed the workspace or are not multiples of 8", n, h, w);
@@ -311,9 +311,8 @@ int gnb_conv_forward(gnb_ctx* ctx, int n, int h, int w, int dense_desc, const bf
         // conv1a stays a separate fp32 kernel in this mode: fusing it into the conv1b kernel (producer warps computing
         // conv1a into the operand ring) measured SLOWER (36 vs 31 ms per 64 pairs): with hi + lo weights resident only
         // three 23 KB operand stages fit, so the producers cannot run a tile ahead of the MMA warp
-        // a1a_ready: the conv1a activation of this pass was already produced on the side stream (gnb_pose_batch)
-        if (!a1a_ready && (rc = gnb_conv1a_x3(ctx, cw.img, n, h, w, cw.a1a))) return rc;
-        if ((rc = conv_layer(ctx, L1B, a1a_ready ? a1a_ready : cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
+        if ((rc = gnb_conv1a_x3(ctx, cw.img, n, h, w, cw.a1a))) return rc;
+        if ((rc = conv_layer(ctx, L1B, cw.a1a, n, h, w, cw.p1, nullptr, 1, 1))) return rc;
         if ((rc = conv_layer(ctx, L2A, cw.p1, n, h / 2, w / 2, cw.a2a, nullptr, 1, 0))) return rc;
         if ((rc = conv_layer(ctx, L2B, cw.a2a, n, h / 2, w / 2, cw.p2, nullptr, 1, 1))) return rc;
         if ((rc = conv_layer(ctx, L3A, cw.p2, n, h / 4, w / 4, cw.a3a, nullptr, 1, 0))) return rc;

@@ -67,73 +67,6 @@ __global__ void __launch_bounds__(256, 4) conv1a_x3_kernel(const uint8_t* __rest
     }
 }
 
-// Thin persistent variant: ONE 128-thread CTA per SM loops over 4 x 32 pixel tiles.  It is launched on a side stream
-// for the reference rasters at the start of a batch call and co-resides with the tensor-core kernels of the query-frame
-// pass (8 K registers and 1 KB of shared memory per SM next to their 52 K / 222 KB): conv1a is an HBM write stream,
-// they are tensor-bound, so the rasters' conv1a disappears from the critical path (gnb_pose_batch, fp32-faithful mode).
-#define X1T_TH 4
-__global__ void __launch_bounds__(128) conv1a_x3_thin_kernel(const uint8_t* __restrict__ img, const float* __restrict__ wt,
-                                                             const float* __restrict__ bias, int n_img, int h, int w, bf16* __restrict__ out) {
-    __shared__ float patch[X1T_TH + 2][X1_TW + 2 + 2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = (lane & 15) * 4, sub = lane >> 4;
-    float wr[9][4], br[4];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) wr[t][j] = wt[t * 64 + c0 + j];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) br[j] = bias[c0 + j];
-    const int tiles_x = (w + X1_TW - 1) / X1_TW, tiles_y = (h + X1T_TH - 1) / X1T_TH;
-    const int total = tiles_x * tiles_y * n_img;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int b = tile / (tiles_x * tiles_y), rem = tile - b * tiles_x * tiles_y;
-        const int y0 = (rem / tiles_x) * X1T_TH, x0 = (rem % tiles_x) * X1_TW;
-        const uint8_t* im = img + (size_t)b * h * w;
-        __syncthreads();
-        for (int i = threadIdx.x; i < (X1T_TH + 2) * (X1_TW + 2); i += 128) {
-            const int ly = i / (X1_TW + 2), lx = i % (X1_TW + 2);
-            const int y = y0 + ly - 1, x = x0 + lx - 1;
-            float f = 0.f;
-            if (y >= 0 && y < h && x >= 0 && x < w) f = __fdiv_rn((float)im[(size_t)y * w + x], 255.0f);
-            patch[ly][lx] = f;
-        }
-        __syncthreads();
-        const int ly = warp, y = y0 + ly;
-        if (y >= h) continue;
-#pragma unroll 4
-        for (int it = 0; it < X1_TW / 2; ++it) {
-            const int lx = it * 2 + sub, x = x0 + lx;
-            float v[9];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) v[t] = patch[ly + t / 3][lx + t % 3];
-            float a[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float acc = 0.f;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wr[t][j], acc);
-                a[j] = fmaxf(acc + br[j], 0.f);
-            }
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
-            const __nv_bfloat162 l0 = __floats2bfloat162_rn(__fsub_rn(a[0], __low2float(h0)), __fsub_rn(a[1], __high2float(h0)));
-            const __nv_bfloat162 l1 = __floats2bfloat162_rn(__fsub_rn(a[2], __low2float(h1)), __fsub_rn(a[3], __high2float(h1)));
-            if (x < w) {
-                bf16* o = out + ((size_t)b * h * w + (size_t)y * w + x) * 128 + c0;
-                *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-                *reinterpret_cast<uint2*>(o + 64) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
-            }
-        }
-    }
-}
-
-// enqueue the thin kernel on `stream` (not the context's main stream; not event-profiled)
-int gnb_conv1a_x3_side(gnb_ctx* ctx, cudaStream_t stream, const uint8_t* img, int n, int h, int w, bf16* out) {
-    conv1a_x3_thin_kernel<<<ctx->sm_count, 128, 0, stream>>>(img, ctx->layers[L1A].w_f32, ctx->layers[L1A].bias, n, h, w, out);
-    GNB_LAUNCH_CHECK(ctx);
-    return GNB_OK;
-}
-
 int gnb_conv1a_x3(gnb_ctx* ctx, const uint8_t* img, int n, int h, int w, bf16* out) {
     dim3 grid(ceil_div(w, X1_TW), ceil_div(h, X1_TH), n);
     GNB_KERNEL(ctx, "conv1a_x3_kernel", conv1a_x3_kernel<<<grid, 256, 0, ctx->stream>>>(img, ctx->layers[L1A].w_f32, ctx->layers[L1A].bias, h, w, out));

@@ -8,6 +8,7 @@
 #   launches <precision>       ncu launch list (gpu__time_duration.sum) of two steps -> gpurun_out/launches_<precision>.csv
 #   ncu <precision> [batch]    ncu --set full of ONE step (batch 16 by default) summarised by tools/ncu_summary.py
 #                              -> gpurun_out/ncu_step_<precision>.{json,md}
+#   ncu_kernel <regex> [precision] [skip]   ncu --set full with source of ONE launch of a kernel -> gpurun_out/ncu_<regex>_{source,raw}.csv, _details.txt
 #   sanitizer                  compute-sanitizer memcheck + racecheck over a small batch call
 #   stream | config5           bench.py --config 4 / 5 on the GPUs of this box (torchrun when --gpus > 1: use run_n)
 #   run_n <N> [bench.py args]  torchrun launch exactly like the driver's (N ranks on one box)
@@ -37,6 +38,13 @@ PY
              timeout 1400 ncu --set full --clock-control none --import-source on --launch-skip $skip --launch-count $count -o /tmp/prof_step_$p \
                python bench.py --steps 1 --warmup 3 --batch $b --cpu-pairs 0 --acc-pairs 0 --precision $p > gpurun_out/ncu_step.log 2>&1
              python tools/ncu_summary.py /tmp/prof_step_$p.ncu-rep gpurun_out/ncu_step_$p.json > gpurun_out/ncu_step_$p.md; tail -3 gpurun_out/ncu_step_$p.md ;;
+  ncu_kernel) k=$1; p=${2:-bf16_fast}; skip=${3:-8}
+             timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip $skip --launch-count 1 -o /tmp/k_$k \
+               python bench.py --steps 1 --warmup 3 --batch 16 --cpu-pairs 0 --acc-pairs 0 --sift-pairs 0 --precision $p > gpurun_out/ncu_kernel.log 2>&1
+             ncu -i /tmp/k_$k.ncu-rep --page source --csv > gpurun_out/ncu_${k}_source.csv 2>/dev/null
+             ncu -i /tmp/k_$k.ncu-rep --page raw --csv > gpurun_out/ncu_${k}_raw.csv 2>/dev/null
+             ncu -i /tmp/k_$k.ncu-rep --page details > gpurun_out/ncu_${k}_details.txt 2>/dev/null
+             ls -la gpurun_out/ncu_${k}_* ;;
   sanitizer) for tool in memcheck racecheck; do
                timeout 1400 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "batch_equals_single or k2 or x3_layers" \
                  > gpurun_out/sanitizer_$tool.log 2>&1; tail -4 gpurun_out/sanitizer_$tool.log; done ;;
