@@ -166,6 +166,9 @@ static int alloc_workspace(gnb_ctx* ctx) {
     rc |= dalloc(ctx, &ctx->nms_hist, slots * 2048);
     rc |= dalloc(ctx, &ctx->nms_level, slots);
     rc |= dalloc(ctx, &ctx->nms_flag, slots);
+    rc |= dalloc(ctx, &ctx->nms_list, n * GNB_NMS_LIST_CAP);
+    rc |= dalloc(ctx, &ctx->nms_list_count, n + 1);   // + the any-redo word
+    rc |= dalloc(ctx, &ctx->nms_sup, 2 * n * (size_t)c.max_image_h * ((c.max_image_w + 31) / 32));
     rc |= dalloc(ctx, &ctx->kp_xy, slots * k * 2);
     rc |= dalloc(ctx, &ctx->kp_score, slots * k);
     rc |= dalloc(ctx, &ctx->kp_count, slots);
@@ -229,7 +232,7 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->match_score, ctx->match_count, ctx->mkp_qry, ctx->mkp_ref, ctx->obj, ctx->hyp, ctx->hyp_count,
                     ctx->inlier_mask, ctx->range_flag, ctx->kmat, ctx->affine, ctx->dem, ctx->out_dev, ctx->stage_a,
                     ctx->stage_b, ctx->c_kp_xy, ctx->c_kp_count, ctx->c_mproj, ctx->c_mlogit, ctx->c_desc, ctx->warp_buf,
-                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->nms_hist, ctx->nms_level, ctx->nms_flag};
+                    ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->nms_hist, ctx->nms_level, ctx->nms_flag, ctx->nms_list, ctx->nms_list_count, ctx->nms_sup};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->out_host) cudaFreeHost(ctx->out_host);

@@ -12,6 +12,7 @@ typedef __nv_bfloat16 bf16;
 
 #define GNB_NUM_LAYERS 12
 #define GNB_CAND_CAP 65536  // NMS survivors kept per image before top-K
+#define GNB_NMS_LIST_CAP 131072   // listed pixels per image of the list-based NMS (more: that image falls back to the tile kernel)
 #define GNB_MAX_KP 4096     // hard ceiling for cfg.max_keypoints
 
 enum LayerId { L1A = 0, L1B, L2A, L2B, L3A, L3B, L4A, L4B, LPA, LPB, LDA, LDB };
@@ -71,6 +72,9 @@ struct gnb_ctx {
     unsigned* nms_hist;             // [slots][2048] score-bit histogram of the sparse NMS (keypoints.cu)
     unsigned* nms_level;            // [slots] per-image level L: only pixels with score bits >= L are processed
     int* nms_flag;                  // [slots] 1 = redo this image from the plain threshold
+    uint2* nms_list;                // [max_batch][GNB_NMS_LIST_CAP] (pixel index, score bits) of the pixels at or above the level
+    int* nms_list_count;            // [max_batch] + 1 (any image to redo)
+    unsigned* nms_sup;              // [2][max_batch][h][ceil(w / 32)] suppression bitmaps (dilated maxima) of rounds 0 and 1
     float* kp_xy;                   // [slots][K][2]
     float* kp_score;                // [slots][K]
     int* kp_count;                  // [slots]

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
 // suppress pixels that are not larger than itself.  Only the K best survivors are kept, and with the shipped weights
 // < 1 % (K = 1024) to 3 % (K = 2048) of the pixels score above the K-th survivor.  So:
 //   1. nms_hist_kernel   histogram of the score bit patterns (every 4th row: the level only steers the work, never the
-//                        result) -> nms_level_kernel picks, per image, a level L with ~32 K pixels at or above it
+//                        result) -> nms_level_kernel picks, per image, a level L with ~16 K pixels at or above it
 //                        (never below the keypoint threshold);
 //   2. nms_sparse_kernel per 64x64 tile + 20 px halo: scores below L enter shared memory as 0, the pixels at or above
 //                        L form a short list, and every stage of simple_nms (window max, suppression dilation, two
@@ -319,7 +319,8 @@ __device__ __forceinline__ void ns_mark_maxima(const NsRegion& R, unsigned* __re
 __global__ void __launch_bounds__(NS_THREADS, 3) nms_sparse_kernel(const float* __restrict__ score, int h, int w, int n_img, float threshold, int border,
                                                                 int slot0, const unsigned* __restrict__ level, const int* __restrict__ first_count,
                                                                 int redo, int k_cap, unsigned thr_bits, unsigned long long* __restrict__ cand_keys,
-                                                                int* __restrict__ cand_count) {
+                                                                int* __restrict__ cand_count, const int* __restrict__ any_redo = nullptr) {
+    if (any_redo && *any_redo == 0) return;
     extern __shared__ float sm[];
     float* S = sm;
     unsigned* MAXM = reinterpret_cast<unsigned*>(S + NS_REG * NS_PITCH);
@@ -338,7 +339,8 @@ __global__ void __launch_bounds__(NS_THREADS, 3) nms_sparse_kernel(const float* 
         if (redo) {
             // second launch: only images whose first pass found fewer than K survivors above a level that was higher than
             // the plain threshold are redone, from the threshold (first_count / level are not written by this launch)
-            if (!(first_count[slot] < k_cap && lv > thr_bits + 1u)) continue;
+            // (redo == 2, list path: first_count holds the decision itself, see nms_redo_prepare_lists)
+            if (redo == 2 ? first_count[slot] == 0 : !(first_count[slot] < k_cap && lv > thr_bits + 1u)) continue;
             lv = thr_bits + 1u;
         }
         const int y0 = (t / tiles_x) * NS_TILE - 20, x0 = (t % tiles_x) * NS_TILE - 20;
@@ -475,6 +477,235 @@ __global__ void __launch_bounds__(NS_THREADS, 3) nms_sparse_kernel(const float* 
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// List-based form of the same sparse NMS — the product path.  The tile kernel above spends its time in the three marking
+// passes of 104x104 regions (62 % of its warp samples; 30 % of all samples wait at its barriers) and repeats the work of
+// a halo pixel in up to four regions.  Here the listed pixels of the WHOLE image are compacted once and every stage of
+// simple_nms is one launch over that list against the score map in L2 (59 MB for 16 frames: it stays resident):
+//   nms_compact_kernel   streams the map once; (pixel index, score bits) of the pixels at or above the level -> nms_list
+//   nms_round_kernel<R>  one lane per listed pixel: 3x3 pre-check, then the warp scans the 9x9 window of the pixels that
+//                        passed.  A new maximum is final (it is emitted as a top-K candidate at once) and ORs its 9x9
+//                        block into the suppression bitmap the NEXT round reads (R = 0 -> SUPA, 1 -> SUPB): no barrier,
+//                        no halo, no shared memory.  Same comparisons on the same values as the tile kernel.
+// An image whose list overflows (ties at the level, flat maps) or that ends with fewer than K survivors above its level
+// is redone from the plain threshold by the tile kernel (nms_redo_prepare_lists -> nms_sparse_kernel(redo)).
+#define NL_PER_THREAD 40   // pixels per thread of the compaction (ten float4 loads in flight)
+
+// (A variant that kept the row-major pixel order inside the list — ballot ranks per step — made this kernel 2x slower,
+// 0.21 vs 0.11 ms per 128 frames, and the round kernels no faster: they wait on load latency, not on L1 tag cycles.)
+template <bool VEC>
+__global__ void __launch_bounds__(256) nms_compact_kernel(const float* __restrict__ score, int hw, int slot0, const unsigned* __restrict__ level,
+                                                          uint2* __restrict__ list, int* __restrict__ list_count) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lv = (int)level[slot0 + b];
+    const float* sc = score + (size_t)b * hw;
+    const int chunk0 = blockIdx.x * (256 * NL_PER_THREAD);
+    unsigned vbits[NL_PER_THREAD];
+    // element e of this thread is pixel pix(e): a float4 per thread and step (VEC) or one float (ragged sizes)
+    auto pix = [&](int e) { return VEC ? chunk0 + ((e >> 2) * 256 + (int)threadIdx.x) * 4 + (e & 3) : chunk0 + e * 256 + (int)threadIdx.x; };
+    if (VEC) {
+#pragma unroll
+        for (int u = 0; u < NL_PER_THREAD / 4; ++u) {
+            const int i = pix(4 * u);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < hw) v = __ldg(reinterpret_cast<const float4*>(sc + i));   // hw % 4 == 0: a vector is inside or outside
+            vbits[4 * u] = __float_as_uint(v.x); vbits[4 * u + 1] = __float_as_uint(v.y);
+            vbits[4 * u + 2] = __float_as_uint(v.z); vbits[4 * u + 3] = __float_as_uint(v.w);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < NL_PER_THREAD; ++e) {
+            const int i = pix(e);
+            vbits[e] = i < hw ? __float_as_uint(__ldg(sc + i)) : 0u;
+        }
+    }
+    // listed <=> bits >= level as signed ints (level >= 1: padding zeros and negative scores never count)
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < NL_PER_THREAD; ++e) cnt += ((int)vbits[e] >= lv) ? 1 : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int t = s_warp[i]; s_warp[i] = tot; tot += t; }
+        s_base = tot ? atomicAdd(&list_count[b], tot) : 0;
+    }
+    __syncthreads();
+    if (cnt == 0) return;
+    int pos = s_base + s_warp[warp] + incl - cnt;
+    uint2* out = list + (size_t)b * GNB_NMS_LIST_CAP;
+#pragma unroll
+    for (int e = 0; e < NL_PER_THREAD; ++e)
+        if ((int)vbits[e] >= lv) {
+            if (pos < GNB_NMS_LIST_CAP) out[pos] = make_uint2((unsigned)pix(e), vbits[e]);
+            ++pos;
+        }
+}
+
+// Latency is what this kernel fights (77 % of its warp samples waited on a load in the first version): every batch of
+// loads is issued back to back from clamped addresses before the first compare, up to FOUR candidates of a warp-iteration
+// are scanned at once (8 lanes each, 11 window positions per lane in flight), and the survivors of a warp are buffered in
+// shared memory so that the candidate counter is bumped once per warp, not once per iteration.
+// Bitmaps: round 0 ORs the 9x9 blocks of its maxima into SUPA and SUPB; round 1 reads SUPA and adds its own to SUPB;
+// round 2 reads SUPB (= dilation of all maxima so far).  Each round reads one bitmap and never the one it writes.
+#define NR_BUF 64   // buffered survivors per warp (flushed when more than half full)
+template <int ROUND>
+__global__ void __launch_bounds__(256) nms_round_kernel(const float* __restrict__ score, int h, int w, int slot0, const uint2* __restrict__ list,
+                                                        const int* __restrict__ list_count, unsigned* __restrict__ sup_a,
+                                                        unsigned* __restrict__ sup_b, int wpr, float threshold, int border,
+                                                        unsigned long long* __restrict__ cand_keys, int* __restrict__ cand_count) {
+    __shared__ unsigned long long s_keys[8][NR_BUF];
+    const int b = blockIdx.y, slot = slot0 + b, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = list_count[b];
+    if (n > GNB_NMS_LIST_CAP) return;   // overflow: this image is redone by the tile kernel
+    const float* sc = score + (size_t)b * h * w;
+    const uint2* li = list + (size_t)b * GNB_NMS_LIST_CAP;
+    const size_t bm = (size_t)b * h * wpr;
+    const unsigned* rd = (ROUND == 2 ? sup_b : sup_a) + bm;     // the bitmap this round reads (none in round 0)
+    unsigned* wa = sup_a + bm;
+    unsigned* wb = sup_b + bm;
+    auto suppressed = [&](int y, int x) -> bool {
+        if (ROUND == 0) return false;
+        return (rd[y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+    };
+    const int grp = lane >> 3, sub = lane & 7;
+    int n_buf = 0;   // warp-uniform
+    auto flush = [&]() {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&cand_count[slot], n_buf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < n_buf; i += 32)
+            if (base + i < GNB_CAND_CAP) cand_keys[(size_t)slot * GNB_CAND_CAP + base + i] = s_keys[warp][i];
+        __syncwarp();
+        n_buf = 0;
+    };
+    for (int e0 = (blockIdx.x * 8 + warp) * 32; e0 < n; e0 += gridDim.x * 256) {
+        const int e = e0 + lane;
+        int py = 0, px = 0;
+        float s = 0.f;
+        bool cand = false;
+        if (e < n) {
+            const uint2 en = li[e];
+            py = (int)en.x / w; px = (int)en.x - py * w;
+            s = __uint_as_float(en.y);
+            cand = !suppressed(py, px);    // rounds 1 and 2: most listed pixels sit inside the 9x9 block of an earlier maximum
+        }
+        if (cand) {
+            // 3x3 pre-check: the eight loads leave together (clamped addresses: a clamped position is the pixel itself or
+            // another member of its 3x3 block, so it changes nothing)
+            const int ym = max(py - 1, 0), yp = min(py + 1, h - 1), xm = max(px - 1, 0), xp = min(px + 1, w - 1);
+            const float* r0 = sc + (size_t)ym * w;
+            const float* r1 = sc + (size_t)py * w;
+            const float* r2 = sc + (size_t)yp * w;
+            const float v0 = __ldg(r0 + xm), v1 = __ldg(r0 + px), v2 = __ldg(r0 + xp), v3 = __ldg(r1 + xm), v4 = __ldg(r1 + xp),
+                        v5 = __ldg(r2 + xm), v6 = __ldg(r2 + px), v7 = __ldg(r2 + xp);
+            if (v0 > s && !suppressed(ym, xm)) cand = false;
+            if (v1 > s && !suppressed(ym, px)) cand = false;
+            if (v2 > s && !suppressed(ym, xp)) cand = false;
+            if (v3 > s && !suppressed(py, xm)) cand = false;
+            if (v4 > s && !suppressed(py, xp)) cand = false;
+            if (v5 > s && !suppressed(yp, xm)) cand = false;
+            if (v6 > s && !suppressed(yp, px)) cand = false;
+            if (v7 > s && !suppressed(yp, xp)) cand = false;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, cand);
+        bool is_max = false;
+        while (todo) {
+            // up to four candidates at once: group g (8 lanes) takes the g-th set bit of `todo`
+            int src = -1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int f = todo ? __ffs(todo) - 1 : -1;
+                if (todo) todo &= todo - 1u;
+                if (g == grp) src = f;
+            }
+            const int sl = src < 0 ? 0 : src;
+            const int cy = __shfl_sync(0xffffffffu, py, sl), cx = __shfl_sync(0xffffffffu, px, sl);
+            const float cs = __shfl_sync(0xffffffffu, s, sl);
+            float wv[11];
+#pragma unroll
+            for (int r = 0; r < 11; ++r) {
+                const int p = min(sub + 8 * r, 80);   // window position (the last lanes repeat position 80)
+                const int yy = min(max(cy + p / 9 - 4, 0), h - 1), xx = min(max(cx + p % 9 - 4, 0), w - 1);
+                wv[r] = src >= 0 ? __ldg(sc + (size_t)yy * w + xx) : 0.f;   // a clamped position is inside the window too: same decision
+            }
+            bool bad = false;
+#pragma unroll
+            for (int r = 0; r < 11; ++r)
+                if (wv[r] > cs) {
+                    if (ROUND == 0) bad = true;
+                    else {
+                        const int p = min(sub + 8 * r, 80);
+                        const int yy = min(max(cy + p / 9 - 4, 0), h - 1), xx = min(max(cx + p % 9 - 4, 0), w - 1);
+                        if (!suppressed(yy, xx)) bad = true;
+                    }
+                }
+            const unsigned bad_lanes = __ballot_sync(0xffffffffu, bad);
+            const bool group_max = src >= 0 && ((bad_lanes >> (8 * grp)) & 0xFFu) == 0u;
+            const unsigned max_groups = __ballot_sync(0xffffffffu, group_max && sub == 0);   // bit 8 g: group g found a maximum
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (!((max_groups >> (8 * g)) & 1u)) continue;
+                const int my = __shfl_sync(0xffffffffu, cy, 8 * g), mx = __shfl_sync(0xffffffffu, cx, 8 * g);
+                const int ms = __shfl_sync(0xffffffffu, src, 8 * g);
+                if (lane == ms) is_max = true;
+                if (ROUND < 2 && lane < 9) {   // rows my - 4 .. my + 4, columns mx - 4 .. mx + 4 (clipped to the image)
+                    const int yy = my - 4 + lane;
+                    if (yy >= 0 && yy < h) {
+                        const int x_lo = max(mx - 4, 0), x_hi = min(mx + 4, w - 1);
+                        const int w0 = x_lo >> 5, w1 = x_hi >> 5;
+                        const unsigned m_lo = 0xffffffffu << (x_lo & 31), m_hi = 0xffffffffu >> (31 - (x_hi & 31));
+                        if (w0 == w1) {
+                            atomicOr(&wb[yy * wpr + w0], m_lo & m_hi);
+                            if (ROUND == 0) atomicOr(&wa[yy * wpr + w0], m_lo & m_hi);
+                        } else {
+                            atomicOr(&wb[yy * wpr + w0], m_lo); atomicOr(&wb[yy * wpr + w1], m_hi);
+                            if (ROUND == 0) { atomicOr(&wa[yy * wpr + w0], m_lo); atomicOr(&wa[yy * wpr + w1], m_hi); }
+                        }
+                    }
+                }
+            }
+        }
+        // a maximum is final whatever the later rounds find: it becomes a top-K candidate now
+        const bool keep = is_max && s > threshold && py >= border && py < h - border && px >= border && px < w - border;
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (ballot) {
+            if (keep) s_keys[warp][n_buf + __popc(ballot & ((1u << lane) - 1))] =
+                          ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(s)) << 32) | (unsigned)(py * w + px);
+            n_buf += __popc(ballot);
+            __syncwarp();
+            if (n_buf > NR_BUF - 32) flush();
+        }
+    }
+    if (n_buf) flush();
+}
+
+// after the three rounds: redo_flag[slot] = 1 (and the candidate counter restarts) when the list overflowed or fewer than
+// K survivors lie above a level that was higher than the plain threshold
+__global__ void nms_redo_prepare_lists(int n, int slot0, int k_cap, unsigned thr_bits, const unsigned* __restrict__ level,
+                                       const int* __restrict__ list_count, int* __restrict__ cand_count, int* __restrict__ redo_flag,
+                                       int* __restrict__ any_redo) {
+    // one CTA: any_redo lets the CTAs of the redo launch leave after ONE load when (as always with real frames) nothing is flagged
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int slot = slot0 + i;
+        const bool redo = list_count[i] > GNB_NMS_LIST_CAP || (cand_count[slot] < k_cap && level[slot] > thr_bits + 1u);
+        redo_flag[slot] = redo ? 1 : 0;
+        if (redo) { cand_count[slot] = 0; mine = 1; }
+    }
+    mine = __syncthreads_or(mine);
+    if (threadIdx.x == 0) *any_redo = mine;
 }
 
 // One CTA per image: exact top-K of the candidate keys (radix select on the 64-bit key, 8 bits per pass, most
@@ -625,7 +856,11 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         // sparse, top-K-aware path (see above)
         const int k_cap = ctx->cfg.max_keypoints;
         const unsigned thr_bits = __float_as_uint_host(ctx->cfg.keypoint_threshold);
-        const unsigned target = (unsigned)((32ll * k_cap + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP);
+        // listed pixels per image the level aims at.  Measured with the shipped weights (oracle, 720p / 1024^2 frames): 16 K
+        // listed pixels hold 1.8 K survivors at K = 1024 and 1.3 K at K = 2048 (8 K: 1.2 K / 0.9 K — too close); an image
+        // that still ends below K is redone from the threshold, so this number only steers the work, never the result
+        static const int level_mult = getenv("GNB_NMS_LEVEL_MULT") ? max(1, atoi(getenv("GNB_NMS_LEVEL_MULT"))) : 16;
+        const unsigned target = (unsigned)(((long long)level_mult * k_cap + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP);
         const int rows = ceil_div(h, NS_HIST_ROW_STEP);
         dim3 hgrid(min(ceil_div(rows * w, 256 * 4), 128), 1, n);
         GNB_KERNEL(ctx, "nms_hist_kernel", nms_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(score, h, w, thr_bits, slot0, ctx->nms_hist));
@@ -635,15 +870,44 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_sparse_kernel, (int)smem));
         const int items = ceil_div(w, NS_TILE) * ceil_div(h, NS_TILE) * n;
         const int grid = min(items, ctx->sm_count * 3);
-        GNB_KERNEL(ctx, "nms_sparse_kernel", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
-            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, nullptr, 0, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
-        // exact redo, from the plain threshold, of the images with fewer than K survivors above their level (rare); its
-        // CTAs decide from the first pass's counts (copied aside: the redo resets and refills cand_count) and exit at once
-        // when there is nothing to redo
-        GNB_KERNEL(ctx, "nms_redo_prepare", nms_redo_prepare<<<ceil_div(n, 64), 64, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->nms_level, ctx->cand_count,
-                                                                                               ctx->nms_flag));
-        GNB_KERNEL(ctx, "nms_sparse_kernel(redo)", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
-            score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 1, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
+        static const int tile_nms = getenv("GNB_NMS_TILES") ? atoi(getenv("GNB_NMS_TILES")) : 0;   // A/B: the tile kernel for the first pass too
+        if (!tile_nms) {
+            // list-based passes over the whole image (see nms_compact_kernel)
+            const int hw = h * w, wpr = ceil_div(w, 32);
+            unsigned* sup_a = ctx->nms_sup;
+            unsigned* sup_b = sup_a + (size_t)n * h * wpr;
+            GNB_CUDA(ctx, cudaMemsetAsync(ctx->nms_list_count, 0, sizeof(int) * n, ctx->stream));
+            GNB_CUDA(ctx, cudaMemsetAsync(sup_a, 0, sizeof(unsigned) * 2 * n * h * wpr, ctx->stream));
+            dim3 cgrid(ceil_div(hw, 256 * NL_PER_THREAD), n);
+            if ((hw & 3) == 0)
+                GNB_KERNEL(ctx, "nms_compact_kernel", nms_compact_kernel<true><<<cgrid, 256, 0, ctx->stream>>>(score, hw, slot0, ctx->nms_level, ctx->nms_list, ctx->nms_list_count));
+            else
+                GNB_KERNEL(ctx, "nms_compact_kernel", nms_compact_kernel<false><<<cgrid, 256, 0, ctx->stream>>>(score, hw, slot0, ctx->nms_level, ctx->nms_list, ctx->nms_list_count));
+            dim3 rgrid(max(1, ceil_div(ctx->sm_count * 8, n)), n);
+            const float thr = ctx->cfg.keypoint_threshold;
+            const int border = ctx->cfg.border;
+            GNB_KERNEL(ctx, "nms_round_kernel<0>", nms_round_kernel<0><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, ctx->nms_list, ctx->nms_list_count, sup_a, sup_b, wpr,
+                                                                                                      thr, border, ctx->cand_keys, ctx->cand_count));
+            GNB_KERNEL(ctx, "nms_round_kernel<1>", nms_round_kernel<1><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, ctx->nms_list, ctx->nms_list_count, sup_a, sup_b, wpr,
+                                                                                                      thr, border, ctx->cand_keys, ctx->cand_count));
+            GNB_KERNEL(ctx, "nms_round_kernel<2>", nms_round_kernel<2><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, ctx->nms_list, ctx->nms_list_count, sup_a, sup_b, wpr,
+                                                                                                      thr, border, ctx->cand_keys, ctx->cand_count));
+            int* any_redo = ctx->nms_list_count + ctx->cfg.max_batch;   // one extra int behind the per-image counts
+            GNB_KERNEL(ctx, "nms_redo_prepare", nms_redo_prepare_lists<<<1, 256, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->nms_level, ctx->nms_list_count,
+                                                                                           ctx->cand_count, ctx->nms_flag, any_redo));
+            GNB_KERNEL(ctx, "nms_sparse_kernel(redo)", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
+                score, h, w, n, thr, border, slot0, ctx->nms_level, ctx->nms_flag, 2, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count, any_redo));
+        } else {
+            GNB_KERNEL(ctx, "nms_sparse_kernel", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
+                score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, nullptr, 0, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
+            // exact redo, from the plain threshold, of the images with fewer than K survivors above their level (rare); its
+            // CTAs decide from the first pass's counts (copied aside: the redo resets and refills cand_count) and exit at once
+            // when there is nothing to redo
+            GNB_KERNEL(ctx, "nms_redo_prepare", nms_redo_prepare<<<ceil_div(n, 64), 64, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->nms_level, ctx->cand_count,
+                                                                                                   ctx->nms_flag));
+            GNB_KERNEL(ctx, "nms_sparse_kernel(redo)", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
+                score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 1, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
+        }
     } else {
         const size_t smem = (size_t)NMS_REG * NMS_REG * (4 * sizeof(float) + 2);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_kernel, (int)smem));

@@ -75,7 +75,7 @@ def test_k1_dense_matches_oracle(rand_blob, rand_params, oracle, impl, hw):
 
 
 # ---- K2: NMS + threshold + border + top-K (bit-exact) -------------------------------------------------
-@pytest.mark.parametrize("case", ["oracle_score", "random", "plateaus", "sparse", "empty", "tiny", "redo_from_threshold", "negative_and_large"])
+@pytest.mark.parametrize("case", ["oracle_score", "random", "plateaus", "sparse", "empty", "tiny", "redo_from_threshold", "negative_and_large", "ragged"])
 def test_k2_keypoint_selection_bit_exact(rand_blob, stages, oracle, case):
     rng = np.random.default_rng(5)
     k = 64
@@ -95,7 +95,7 @@ def test_k2_keypoint_selection_bit_exact(rand_blob, stages, oracle, case):
     elif case == "empty":
         score = np.full((64, 64), 0.001, np.float32)
     elif case == "redo_from_threshold":
-        # the sparse NMS picks a level with ~32 K pixels above it: here those all sit on ONE smooth bump (a single
+        # the sparse NMS picks a level with ~16 K pixels above it: here those all sit on ONE smooth bump (a single
         # survivor), so the image must be redone from the plain threshold to find the low isolated peaks
         yy, xx = np.mgrid[0:256, 0:320].astype(np.float32)
         score = (0.9 * np.exp(-((yy - 120) ** 2 + (xx - 160) ** 2) / (2 * 80.0 ** 2))).astype(np.float32)
@@ -105,6 +105,9 @@ def test_k2_keypoint_selection_bit_exact(rand_blob, stages, oracle, case):
             if score[y, x] == 0:
                 score[y, x] = np.float32(0.006 + 0.1 * rng.random())
         k = 300
+    elif case == "ragged":
+        score = (rng.random((97, 131)) ** 3).astype(np.float32) * 0.3       # h w odd: the scalar load paths
+        k = 150
     elif case == "negative_and_large":
         score = (rng.standard_normal((96, 160)) * 0.7).astype(np.float32)     # negative scores and scores >= 2
         score[10, 20] = 3.5; score[50, 80] = 2.0; score[51, 81] = 2.0
@@ -124,6 +127,34 @@ def test_k2_keypoint_selection_bit_exact(rand_blob, stages, oracle, case):
     np.testing.assert_array_equal(sc[: n.value], sc_ref)
     if case == "empty":
         assert n.value == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", ["one_bucket", "ties_at_level", "two_images"])
+def test_k2_list_overflow_and_batches_bit_exact(rand_blob, oracle, case):
+    """The list-based NMS keeps at most GNB_NMS_LIST_CAP = 131072 listed pixels per image: a map whose pixels all fall in
+    one histogram bucket (the level cannot separate them) or that ties at the level overflows the list and is redone by
+    the tile kernel from the plain threshold — same keypoints, bit for bit.  `two_images`: an overflowing map and then a
+    normal one through the same context (the per-call list state restarts)."""
+    rng = np.random.default_rng(77)
+    h, w, k = 448, 512, 256
+    if case == "one_bucket":
+        maps = [(0.5 + 0.01 * rng.random((h, w))).astype(np.float32)]          # 229 K pixels inside one 6 % bucket
+    elif case == "ties_at_level":
+        m = (np.round(rng.random((h, w)) * 3) / 8).astype(np.float32)           # four values: huge tied plateaus
+        m[rng.random((h, w)) < 0.0005] = 0.9                                    # and a few isolated peaks
+        maps = [m]
+    else:
+        maps = [(0.5 + 0.01 * rng.random((h, w))).astype(np.float32), (rng.random((h, w)) ** 4 * 0.4).astype(np.float32)]
+    ctx = Context(Config(max_batch=2, max_image_h=h, max_image_w=w, max_keypoints=k, conv_impl=1, match_impl=1), weights=rand_blob)
+    for m in maps:       # one at a time through the public single-map call
+        m = np.ascontiguousarray(m)
+        xy = np.empty((k, 2), np.float32); sc = np.empty((k,), np.float32); n = C.c_int(0)
+        ctx.check(ctx._lib.gnb_select_keypoints(ctx.handle, ptr(m), h, w, ptr(xy), ptr(sc), k, C.byref(n)))
+        xy_ref, sc_ref = oracle.nms_ref.select_keypoints(m, max_keypoints=k)
+        assert n.value == len(xy_ref)
+        np.testing.assert_array_equal(xy[: n.value], xy_ref)
+        np.testing.assert_array_equal(sc[: n.value], sc_ref)
     ctx.close()
 
 
