@@ -163,7 +163,7 @@ static int alloc_workspace(gnb_ctx* ctx) {
     ctx->kp_slots = (int)slots;
     rc |= dalloc(ctx, &ctx->cand_keys, slots * GNB_CAND_CAP);
     rc |= dalloc(ctx, &ctx->cand_count, slots);
-    rc |= dalloc(ctx, &ctx->nms_hist, slots * 2048);
+    rc |= dalloc(ctx, &ctx->nms_hist, slots * 2048 + slots);   // + one ticket word per slot
     rc |= dalloc(ctx, &ctx->nms_level, slots);
     rc |= dalloc(ctx, &ctx->nms_flag, slots);
     rc |= dalloc(ctx, &ctx->nms_list, n * GNB_NMS_LIST_CAP);
@@ -211,7 +211,7 @@ static int alloc_workspace(gnb_ctx* ctx) {
     for (size_t i = 0; i < cc; ++i) { ctx->cache_ids[i] = -1; ctx->cache_lru[i] = 0; }
     ctx->cache_clock = 0;
     GNB_CUDA(ctx, cudaMemset(ctx->kp_count, 0, slots * sizeof(int)));
-    GNB_CUDA(ctx, cudaMemset(ctx->nms_hist, 0, slots * 2048 * sizeof(unsigned)));
+    GNB_CUDA(ctx, cudaMemset(ctx->nms_hist, 0, (slots * 2048 + slots) * sizeof(unsigned)));
     GNB_CUDA(ctx, cudaMemset(ctx->mproj, 0, slots * k * 256 * sizeof(bf16)));
     GNB_CUDA(ctx, cudaMemset(ctx->kp_xy, 0, slots * k * 2 * sizeof(float)));
     GNB_CUDA(ctx, cudaMallocHost((void**)&ctx->out_host, n * sizeof(PairOut)));

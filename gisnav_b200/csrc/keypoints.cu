@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
 // the survivors of simple_nms with score > T are unchanged when every pixel <= T is replaced by 0 — a pixel can only
 // suppress pixels that are not larger than itself.  Only the K best survivors are kept, and with the shipped weights
 // < 1 % (K = 1024) to 3 % (K = 2048) of the pixels score above the K-th survivor.  So:
-//   1. nms_hist_kernel   histogram of the score bit patterns (every 4th row: the level only steers the work, never the
-//                        result) -> nms_level_kernel picks, per image, a level L with ~16 K pixels at or above it
+//   1. nms_hist_kernel   histogram of the score bit patterns (every 8th row: the level only steers the work, never the
+//                        result); its last CTA per image picks a level L with ~16 K pixels at or above it
 //                        (never below the keypoint threshold);
 //   2. nms_sparse_kernel per 64x64 tile + 20 px halo: scores below L enter shared memory as 0, the pixels at or above
 //                        L form a short list, and every stage of simple_nms (window max, suppression dilation, two
@@ -146,12 +146,21 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
 #define NS_BUCKETS 2048          // score bits >> 19: sign + exponent + 4 mantissa bits of a float in [0, 2)
 #define NS_HIST_ROW_STEP 8
 
+// The last CTA of an image to finish (ticket) turns the merged histogram into that image's level: the highest bucket
+// edge with >= target sampled pixels at or above it, never below the keypoint threshold — and clears histogram and ticket
+// for the next call.  (Plain shared-memory atomics: `__match_any_sync` aggregation was measured slower, here and in
+// `topk_kernel`.)
 __global__ void __launch_bounds__(256) nms_hist_kernel(const float* __restrict__ score, int h, int w, unsigned thr_bits, int slot0,
-                                                       unsigned* __restrict__ hist) {
+                                                       unsigned* __restrict__ hist, unsigned* __restrict__ ticket, unsigned target_sampled,
+                                                       unsigned* __restrict__ level, int* __restrict__ flag, int* __restrict__ cand_count,
+                                                       int* __restrict__ list_count) {
     __shared__ unsigned sh[NS_BUCKETS];
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_edge;
+    __shared__ int s_last;
     for (int i = threadIdx.x; i < NS_BUCKETS; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
-    const int b = blockIdx.z;
+    const int b = blockIdx.z, slot = slot0 + b;
     const float* sc = score + (size_t)b * h * w;
     const int rows = (h + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP;
     const int total = rows * w;
@@ -168,53 +177,54 @@ __global__ void __launch_bounds__(256) nms_hist_kernel(const float* __restrict__
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool act = (int)bits[u] > (int)thr_bits && bits[u] < 0x40000000u;   // thr < score < 2
-            if (act) {
-                const unsigned bucket = bits[u] >> 19;
-                const unsigned peers = __match_any_sync(__activemask(), bucket);
-                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bucket], (unsigned)__popc(peers));
-            }
+        for (int u = 0; u < 4; ++u)
+            if ((int)bits[u] > (int)thr_bits && bits[u] < 0x40000000u) atomicAdd(&sh[bits[u] >> 19], 1u);   // thr < score < 2
+    }
+    __syncthreads();
+    unsigned* hs = hist + (size_t)slot * NS_BUCKETS;
+    for (int i = threadIdx.x; i < NS_BUCKETS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hs[i], sh[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ticket[slot], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- level: thread t owns buckets [8 t, 8 t + 8); suffix sums over threads (thread 255 holds the highest buckets)
+    constexpr int PER = NS_BUCKETS / 256;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned cnt[PER], mine = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { cnt[i] = __ldcg(&hs[threadIdx.x * PER + i]); mine += cnt[i]; }
+    unsigned incl = mine;   // inclusive suffix sum inside the warp (lanes above this one)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
+    }
+    if (lane == 0) s_warp[warp] = incl;
+    if (threadIdx.x == 0) s_edge = 0u;
+    __syncthreads();
+    unsigned above = incl - mine;   // pixels in buckets strictly above this thread's
+    for (int wi = warp + 1; wi < 8; ++wi) above += s_warp[wi];
+    if (above < target_sampled && above + mine >= target_sampled) {   // the crossing thread (at most one)
+        unsigned acc = above;
+        for (int i = PER - 1; i >= 0; --i) {
+            acc += cnt[i];
+            if (acc >= target_sampled) { s_edge = (unsigned)(threadIdx.x * PER + i); break; }
         }
     }
     __syncthreads();
-    unsigned* out = hist + (size_t)(slot0 + b) * NS_BUCKETS;
-    for (int i = threadIdx.x; i < NS_BUCKETS; i += blockDim.x)
-        if (sh[i]) atomicAdd(&out[i], sh[i]);
-}
-
-// one warp per image: highest bucket edge with >= target sampled pixels at or above it
-__global__ void __launch_bounds__(32) nms_level_kernel(unsigned* __restrict__ hist, int slot0, unsigned target_sampled, unsigned thr_bits,
-                                                       unsigned* __restrict__ level, int* __restrict__ flag) {
-    const int slot = slot0 + blockIdx.x, lane = threadIdx.x;
-    unsigned* hs = hist + (size_t)slot * NS_BUCKETS;
-    constexpr int PER = NS_BUCKETS / 32;
-    unsigned mine = 0;
-    for (int i = 0; i < PER; ++i) mine += hs[lane * PER + i];
-    // suffix sums over lanes (lane 31 holds the highest buckets)
-    unsigned above = 0;   // pixels in lanes strictly above this one
-    for (int l = 31; l >= 0; --l) {
-        const unsigned v = __shfl_sync(0xffffffffu, mine, l);
-        if (lane < l) above += v;
-    }
-    // the crossing lane: above < target <= above + mine
-    const bool crossing = above < target_sampled && above + mine >= target_sampled;
-    unsigned edge = 0;   // bucket index; 0 = no crossing (fewer pixels than the target above the threshold)
-    if (crossing) {
-        unsigned acc = above;
-        for (int i = PER - 1; i >= 0; --i) {
-            acc += hs[lane * PER + i];
-            if (acc >= target_sampled) { edge = (unsigned)(lane * PER + i); break; }
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) edge = max(edge, __shfl_xor_sync(0xffffffffu, edge, o));
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         const unsigned lo = thr_bits + 1u;                    // score > threshold  <=>  bits >= thr_bits + 1 (non-negative floats)
-        const unsigned lv = max(edge << 19, lo);
-        level[slot] = lv;
+        level[slot] = max(s_edge << 19, lo);                  // no crossing (fewer pixels than the target): the threshold itself
         flag[slot] = 0;
+        ticket[slot] = 0u;
+        cand_count[slot] = 0;      // the per-call counters restart here instead of in two memset launches
+        list_count[b] = 0;
     }
-    for (int i = lane; i < NS_BUCKETS; i += 32) hs[i] = 0u;   // ready for the next pass
+#pragma unroll
+    for (int i = 0; i < PER; ++i) hs[threadIdx.x * PER + i] = 0u;   // ready for the next call
 }
 
 // first_count[slot] = survivors of the first pass; the counters of the images about to be redone restart at 0
@@ -850,7 +860,6 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         GNB_SET_ERR(ctx, "nms_radius %d too large for the NMS halo", ctx->cfg.nms_radius);
         return GNB_E_INVALID;
     }
-    GNB_CUDA(ctx, cudaMemsetAsync(ctx->cand_count + slot0, 0, sizeof(int) * n, ctx->stream));
     static const int dense_nms = getenv("GNB_NMS_DENSE") ? atoi(getenv("GNB_NMS_DENSE")) : 0;   // A/B: the dense generic-radius kernel
     if (ctx->cfg.nms_radius == 4 && ctx->cfg.keypoint_threshold >= 0.f && !dense_nms) {
         // sparse, top-K-aware path (see above)
@@ -862,9 +871,11 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         static const int level_mult = getenv("GNB_NMS_LEVEL_MULT") ? max(1, atoi(getenv("GNB_NMS_LEVEL_MULT"))) : 16;
         const unsigned target = (unsigned)(((long long)level_mult * k_cap + NS_HIST_ROW_STEP - 1) / NS_HIST_ROW_STEP);
         const int rows = ceil_div(h, NS_HIST_ROW_STEP);
-        dim3 hgrid(min(ceil_div(rows * w, 256 * 4), 128), 1, n);
-        GNB_KERNEL(ctx, "nms_hist_kernel", nms_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(score, h, w, thr_bits, slot0, ctx->nms_hist));
-        GNB_KERNEL(ctx, "nms_level_kernel", nms_level_kernel<<<n, 32, 0, ctx->stream>>>(ctx->nms_hist, slot0, target, thr_bits, ctx->nms_level, ctx->nms_flag));
+        // few CTAs per image when there are many images: every CTA ends with a 2048-bucket merge into the global histogram
+        dim3 hgrid(min(ceil_div(rows * w, 256 * 4), max(8, min(128, ceil_div(ctx->sm_count * 4, n)))), 1, n);
+        GNB_KERNEL(ctx, "nms_hist_kernel", nms_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(score, h, w, thr_bits, slot0, ctx->nms_hist,
+                                                                                           ctx->nms_hist + (size_t)ctx->kp_slots * NS_BUCKETS, target, ctx->nms_level, ctx->nms_flag,
+                                                                                           ctx->cand_count, ctx->nms_list_count));
         const size_t smem = (size_t)NS_REG * NS_PITCH * sizeof(float) + 3 * NS_REG * NS_WORDS * sizeof(unsigned) +
                             (size_t)(NS_LIST_CAP + NS_SURV_CAP) * sizeof(unsigned short);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_sparse_kernel, (int)smem));
@@ -876,7 +887,6 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
             const int hw = h * w, wpr = ceil_div(w, 32);
             unsigned* sup_a = ctx->nms_sup;
             unsigned* sup_b = sup_a + (size_t)n * h * wpr;
-            GNB_CUDA(ctx, cudaMemsetAsync(ctx->nms_list_count, 0, sizeof(int) * n, ctx->stream));
             GNB_CUDA(ctx, cudaMemsetAsync(sup_a, 0, sizeof(unsigned) * 2 * n * h * wpr, ctx->stream));
             dim3 cgrid(ceil_div(hw, 256 * NL_PER_THREAD), n);
             if ((hw & 3) == 0)
@@ -909,6 +919,7 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
                 score, h, w, n, ctx->cfg.keypoint_threshold, ctx->cfg.border, slot0, ctx->nms_level, ctx->nms_flag, 1, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count));
         }
     } else {
+        GNB_CUDA(ctx, cudaMemsetAsync(ctx->cand_count + slot0, 0, sizeof(int) * n, ctx->stream));
         const size_t smem = (size_t)NMS_REG * NMS_REG * (4 * sizeof(float) + 2);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_kernel, (int)smem));
         dim3 grid(ceil_div(w, NMS_TILE), ceil_div(h, NMS_TILE), n);
