@@ -1,6 +1,7 @@
 // api.cu — C ABI of libgisnav_b200.so (include/gisnav_b200.h): context lifetime, workspace, the
 // three reference call sites (detectAndCompute / matcher / compute_pose), the fused batch path
 // and the stage-isolated hooks used by the parity tests.
+#include <utility>
 #include "common.cuh"
 
 #include <nvtx3/nvToolsExt.h>
@@ -134,17 +135,12 @@ static int dalloc(gnb_ctx* ctx, T** p, size_t count) {
     return GNB_OK;
 }
 
-static int alloc_workspace(gnb_ctx* ctx) {
-    const gnb_config& c = ctx->cfg;
-    ConvWorkspace& cw = ctx->cw;
-    const size_t n = c.max_batch, px = (size_t)c.max_image_h * c.max_image_w;
-    cw.cap_images = c.max_batch;
-    cw.cap_pixels = px;
+#define GNB_OVERLAP_IMAGES 2
+
+// the activation buffers of one pass over n images of at most px pixels
+static int alloc_activations(gnb_ctx* ctx, ConvWorkspace& cw, size_t n, size_t px) {
+    const size_t pf = ctx->cfg.precision == 1 ? 2 : 1;   // fp32-faithful mode: every activation is a (hi, lo) pair of bf16
     int rc = 0;
-    rc |= dalloc(ctx, &cw.img_a, n * px);
-    rc |= dalloc(ctx, &cw.img_b, n * px);
-    cw.img = cw.img_a;
-    const size_t pf = c.precision == 1 ? 2 : 1;   // fp32-faithful mode: every activation is a (hi, lo) pair of bf16
     rc |= dalloc(ctx, &cw.a1a, n * px * 64 * pf);
     rc |= dalloc(ctx, &cw.p1, n * px / 4 * 64 * pf);
     rc |= dalloc(ctx, &cw.a2a, n * px / 4 * 64 * pf);
@@ -158,6 +154,26 @@ static int alloc_workspace(gnb_ctx* ctx) {
     rc |= dalloc(ctx, &cw.semi, n * px / 64 * 65);
     rc |= dalloc(ctx, &cw.score, n * px);
     rc |= dalloc(ctx, &cw.dense, n * px / 64 * 256);
+    return rc;
+}
+
+static int alloc_workspace(gnb_ctx* ctx) {
+    const gnb_config& c = ctx->cfg;
+    ConvWorkspace& cw = ctx->cw;
+    const size_t n = c.max_batch, px = (size_t)c.max_image_h * c.max_image_w;
+    cw.cap_images = c.max_batch;
+    cw.cap_pixels = px;
+    int rc = 0;
+    rc |= dalloc(ctx, &cw.img_a, n * px);
+    rc |= dalloc(ctx, &cw.img_b, n * px);
+    cw.img = cw.img_a;
+    rc |= alloc_activations(ctx, cw, n, px);
+    // small batches (the per-message case of the reference node) run the raster chain on a second stream next to the frame
+    // chain: that needs its own activation buffers, for up to GNB_OVERLAP_IMAGES images
+    ctx->overlap_images = (int)(n < GNB_OVERLAP_IMAGES ? n : GNB_OVERLAP_IMAGES);
+    ctx->cw2 = cw;
+    rc |= alloc_activations(ctx, ctx->cw2, ctx->overlap_images, px);
+    ctx->cw2.cap_images = ctx->overlap_images;
     if (rc) return GNB_E_CUDA;
     const size_t slots = 2 * n, k = c.max_keypoints, it = c.ransac_iters;
     ctx->kp_slots = (int)slots;
@@ -166,9 +182,10 @@ static int alloc_workspace(gnb_ctx* ctx) {
     rc |= dalloc(ctx, &ctx->nms_hist, slots * 2048 + slots);   // + one ticket word per slot
     rc |= dalloc(ctx, &ctx->nms_level, slots);
     rc |= dalloc(ctx, &ctx->nms_flag, slots);
-    rc |= dalloc(ctx, &ctx->nms_list, n * GNB_NMS_LIST_CAP);
-    rc |= dalloc(ctx, &ctx->nms_list_count, n + 1);   // + the any-redo word
-    rc |= dalloc(ctx, &ctx->nms_sup, 2 * n * (size_t)c.max_image_h * ((c.max_image_w + 31) / 32));
+    rc |= dalloc(ctx, &ctx->nms_list, slots * GNB_NMS_LIST_CAP);
+    rc |= dalloc(ctx, &ctx->nms_list_count, 2 * slots);   // counts, then the any-redo words
+    ctx->nms_sup_words = (size_t)c.max_image_h * ((c.max_image_w + 31) / 32);   // one bitmap of one image
+    rc |= dalloc(ctx, &ctx->nms_sup, slots * 2 * ctx->nms_sup_words);
     rc |= dalloc(ctx, &ctx->kp_xy, slots * k * 2);
     rc |= dalloc(ctx, &ctx->kp_score, slots * k);
     rc |= dalloc(ctx, &ctx->kp_count, slots);
@@ -235,6 +252,13 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
                     ctx->mproj_f32, ctx->c_mproj_f32, ctx->c_mproj_x3, ctx->nms_hist, ctx->nms_level, ctx->nms_flag, ctx->nms_list, ctx->nms_list_count, ctx->nms_sup};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    {
+        ConvWorkspace& c2 = ctx->cw2;
+        void* a[] = {c2.a1a, c2.p1, c2.a2a, c2.p2, c2.a3a, c2.p3, c2.a4a, c2.a4b, c2.apa, c2.ada, c2.semi, c2.score, c2.dense};
+        void* b[] = {cw.a1a, cw.p1, cw.a2a, cw.p2, cw.a3a, cw.p3, cw.a4a, cw.a4b, cw.apa, cw.ada, cw.semi, cw.score, cw.dense};
+        for (int i = 0; i < 13; ++i)
+            if (a[i] && a[i] != b[i]) cudaFree(a[i]);
+    }
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
     gnb_tc_state_free(ctx);
     delete[] ctx->cache_ids;
@@ -248,7 +272,9 @@ extern "C" void gnb_destroy(gnb_ctx* ctx) {
     if (ctx->ev_frames) cudaEventDestroy(ctx->ev_frames);
     if (ctx->ev_tiles) cudaEventDestroy(ctx->ev_tiles);
     if (ctx->ev_params) cudaEventDestroy(ctx->ev_params);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -294,6 +320,8 @@ extern "C" int gnb_create(const gnb_config* cfg, const void* weights, size_t nby
     if (cudaSetDevice(device) != cudaSuccess) { GNB_SET_ERR(ctx, "cudaSetDevice failed"); return fail(GNB_E_CUDA); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_frames, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_tiles, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_params, cudaEventDisableTiming) != cudaSuccess) {
@@ -582,6 +610,7 @@ extern "C" int gnb_pose_batch(gnb_ctx* ctx, int batch, const uint8_t* frames, in
     if (rc < 0) {
         // an error path must not leave copies of the caller's buffers in flight: the caller may free or reuse them
         cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream2);
         cudaStreamSynchronize(ctx->stream);
     }
     return rc;
@@ -606,6 +635,20 @@ static int pose_batch_impl(gnb_ctx* ctx, int batch, const uint8_t* frames, int h
     GNB_CUDA(ctx, cudaMemcpyAsync(ctx->affine, affine12, sizeof(double) * 12 * batch, kin, cs));
     if (dems) GNB_CUDA(ctx, cudaMemcpyAsync(ctx->dem, dems, (size_t)batch * ht * wt, kin, cs));
     GNB_CUDA(ctx, cudaEventRecord(ctx->ev_params, cs));
+    // Small batches (one pair per message is what the reference node sends): most kernels of one image leave SMs idle
+    // (topk: one CTA; the NMS passes, the descriptor head, the 1/8-resolution layers: a fraction of a wave), so the raster
+    // chain K1-K3 runs on a second stream with its own activation buffers, next to the frame chain, and joins before K4.
+    // Large batches fill the GPU by themselves and stay serial: co-running kernels there was measured slower.
+    static const int no_overlap = getenv("GNB_NO_OVERLAP") ? atoi(getenv("GNB_NO_OVERLAP")) : 0;
+    const bool overlap = batch <= ctx->overlap_images && !ctx->prof_on && !no_overlap;
+    struct Restore {   // the raster chain borrows ctx->stream / ctx->cw: put them back on every exit path
+        gnb_ctx* c; cudaStream_t s; bool active;
+        ~Restore() { if (active) { c->stream = s; std::swap(c->cw, c->cw2); } }
+    } restore{ctx, ctx->stream, false};
+    if (overlap) {   // whatever an earlier call left running on the main stream is ordered before the second stream's work
+        GNB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));
+        GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
+    }
     // query frames -> slots [0, batch)
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_frames, 0));
     cw.img = cw.img_a;
@@ -619,6 +662,11 @@ static int pose_batch_impl(gnb_ctx* ctx, int batch, const uint8_t* frames, int h
         if ((rc = gnb_describe(ctx, batch, hq, wq, 0))) return rc;
     }
     // reference rasters -> slots [max_batch, max_batch + batch)
+    if (overlap) {
+        std::swap(ctx->cw, ctx->cw2);
+        ctx->stream = ctx->stream2;
+        restore.active = true;
+    }
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tiles, 0));
     {
         GnbRange r1("K1 dense stack (rasters)");
@@ -631,6 +679,13 @@ static int pose_batch_impl(gnb_ctx* ctx, int batch, const uint8_t* frames, int h
         GnbRange r2("K2+K3 keypoints + descriptors (rasters)");
         if ((rc = gnb_kp_select(ctx, ctx->cw.score, batch, ht, wt, sb))) return rc;
         if ((rc = gnb_describe(ctx, batch, ht, wt, sb))) return rc;
+    }
+    if (overlap) {
+        GNB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+        ctx->stream = restore.s;
+        std::swap(ctx->cw, ctx->cw2);
+        restore.active = false;
+        GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
     GNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_params, 0));
     {

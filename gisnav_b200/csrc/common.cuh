@@ -54,6 +54,8 @@ struct gnb_ctx {
     int sm_count;
     cudaStream_t stream;
     cudaStream_t copy_stream;           // H2D staging of the batch path, overlapped with compute
+    cudaStream_t stream2;               // small batches: the raster chain (K1-K3) runs here, concurrently with the frame chain
+    cudaEvent_t ev_join;
     cudaEvent_t ev_frames, ev_tiles, ev_params;
     char err[512];
     int64_t launches;
@@ -65,6 +67,8 @@ struct gnb_ctx {
     bf16* match_mw;   // [256]
     float match_mb;
     ConvWorkspace cw;
+    ConvWorkspace cw2;                  // second set of activation buffers for `overlap_images` images (0: none), see stream2
+    int overlap_images;
     // keypoints: slots 0..2*max_batch-1 (frames then tiles)
     int kp_slots;
     unsigned long long* cand_keys;  // [slots][GNB_CAND_CAP]
@@ -72,9 +76,10 @@ struct gnb_ctx {
     unsigned* nms_hist;             // [slots][2048] score-bit histogram of the sparse NMS (keypoints.cu)
     unsigned* nms_level;            // [slots] per-image level L: only pixels with score bits >= L are processed
     int* nms_flag;                  // [slots] 1 = redo this image from the plain threshold
-    uint2* nms_list;                // [max_batch][GNB_NMS_LIST_CAP] (pixel index, score bits) of the pixels at or above the level
-    int* nms_list_count;            // [max_batch] + 1 (any image to redo)
-    unsigned* nms_sup;              // [2][max_batch][h][ceil(w / 32)] suppression bitmaps (dilated maxima) of rounds 0 and 1
+    uint2* nms_list;                // [slots][GNB_NMS_LIST_CAP] (pixel index, score bits) of the pixels at or above the level
+    int* nms_list_count;            // [slots] listed pixels, then [slots] "any image of the call starting at this slot to redo"
+    unsigned* nms_sup;              // [slots][2][nms_sup_words] suppression bitmaps; a call uses the region of its first slot as [2][n][h][ceil(w / 32)]
+    size_t nms_sup_words;           // words of ONE bitmap of ONE image at the configured maximum size (an odd aspect ratio that needs more uses the tile kernel)
     float* kp_xy;                   // [slots][K][2]
     float* kp_score;                // [slots][K]
     int* kp_count;                  // [slots]

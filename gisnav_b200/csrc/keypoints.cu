@@ -875,35 +875,38 @@ int gnb_kp_select(gnb_ctx* ctx, const float* score, int n, int h, int w, int slo
         dim3 hgrid(min(ceil_div(rows * w, 256 * 4), max(8, min(128, ceil_div(ctx->sm_count * 4, n)))), 1, n);
         GNB_KERNEL(ctx, "nms_hist_kernel", nms_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(score, h, w, thr_bits, slot0, ctx->nms_hist,
                                                                                            ctx->nms_hist + (size_t)ctx->kp_slots * NS_BUCKETS, target, ctx->nms_level, ctx->nms_flag,
-                                                                                           ctx->cand_count, ctx->nms_list_count));
+                                                                                           ctx->cand_count, ctx->nms_list_count + slot0));
         const size_t smem = (size_t)NS_REG * NS_PITCH * sizeof(float) + 3 * NS_REG * NS_WORDS * sizeof(unsigned) +
                             (size_t)(NS_LIST_CAP + NS_SURV_CAP) * sizeof(unsigned short);
         GNB_CUDA(ctx, gnb_func_smem(ctx, nms_sparse_kernel, (int)smem));
         const int items = ceil_div(w, NS_TILE) * ceil_div(h, NS_TILE) * n;
         const int grid = min(items, ctx->sm_count * 3);
         static const int tile_nms = getenv("GNB_NMS_TILES") ? atoi(getenv("GNB_NMS_TILES")) : 0;   // A/B: the tile kernel for the first pass too
-        if (!tile_nms) {
+        if (!tile_nms && (size_t)h * ceil_div(w, 32) <= ctx->nms_sup_words) {
             // list-based passes over the whole image (see nms_compact_kernel)
             const int hw = h * w, wpr = ceil_div(w, 32);
-            unsigned* sup_a = ctx->nms_sup;
+            // per-call scratch lives at the call's first slot, so that two calls on different slot ranges can run concurrently
+            unsigned* sup_a = ctx->nms_sup + (size_t)slot0 * 2 * ctx->nms_sup_words;
             unsigned* sup_b = sup_a + (size_t)n * h * wpr;
+            uint2* lists = ctx->nms_list + (size_t)slot0 * GNB_NMS_LIST_CAP;
+            int* list_count = ctx->nms_list_count + slot0;
             GNB_CUDA(ctx, cudaMemsetAsync(sup_a, 0, sizeof(unsigned) * 2 * n * h * wpr, ctx->stream));
             dim3 cgrid(ceil_div(hw, 256 * NL_PER_THREAD), n);
             if ((hw & 3) == 0)
-                GNB_KERNEL(ctx, "nms_compact_kernel", nms_compact_kernel<true><<<cgrid, 256, 0, ctx->stream>>>(score, hw, slot0, ctx->nms_level, ctx->nms_list, ctx->nms_list_count));
+                GNB_KERNEL(ctx, "nms_compact_kernel", nms_compact_kernel<true><<<cgrid, 256, 0, ctx->stream>>>(score, hw, slot0, ctx->nms_level, lists, list_count));
             else
-                GNB_KERNEL(ctx, "nms_compact_kernel", nms_compact_kernel<false><<<cgrid, 256, 0, ctx->stream>>>(score, hw, slot0, ctx->nms_level, ctx->nms_list, ctx->nms_list_count));
+                GNB_KERNEL(ctx, "nms_compact_kernel", nms_compact_kernel<false><<<cgrid, 256, 0, ctx->stream>>>(score, hw, slot0, ctx->nms_level, lists, list_count));
             dim3 rgrid(max(1, ceil_div(ctx->sm_count * 8, n)), n);
             const float thr = ctx->cfg.keypoint_threshold;
             const int border = ctx->cfg.border;
-            GNB_KERNEL(ctx, "nms_round_kernel<0>", nms_round_kernel<0><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, ctx->nms_list, ctx->nms_list_count, sup_a, sup_b, wpr,
+            GNB_KERNEL(ctx, "nms_round_kernel<0>", nms_round_kernel<0><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, lists, list_count, sup_a, sup_b, wpr,
                                                                                                       thr, border, ctx->cand_keys, ctx->cand_count));
-            GNB_KERNEL(ctx, "nms_round_kernel<1>", nms_round_kernel<1><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, ctx->nms_list, ctx->nms_list_count, sup_a, sup_b, wpr,
+            GNB_KERNEL(ctx, "nms_round_kernel<1>", nms_round_kernel<1><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, lists, list_count, sup_a, sup_b, wpr,
                                                                                                       thr, border, ctx->cand_keys, ctx->cand_count));
-            GNB_KERNEL(ctx, "nms_round_kernel<2>", nms_round_kernel<2><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, ctx->nms_list, ctx->nms_list_count, sup_a, sup_b, wpr,
+            GNB_KERNEL(ctx, "nms_round_kernel<2>", nms_round_kernel<2><<<rgrid, 256, 0, ctx->stream>>>(score, h, w, slot0, lists, list_count, sup_a, sup_b, wpr,
                                                                                                       thr, border, ctx->cand_keys, ctx->cand_count));
-            int* any_redo = ctx->nms_list_count + ctx->cfg.max_batch;   // one extra int behind the per-image counts
-            GNB_KERNEL(ctx, "nms_redo_prepare", nms_redo_prepare_lists<<<1, 256, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->nms_level, ctx->nms_list_count,
+            int* any_redo = ctx->nms_list_count + ctx->kp_slots + slot0;
+            GNB_KERNEL(ctx, "nms_redo_prepare", nms_redo_prepare_lists<<<1, 256, 0, ctx->stream>>>(n, slot0, k_cap, thr_bits, ctx->nms_level, list_count,
                                                                                            ctx->cand_count, ctx->nms_flag, any_redo));
             GNB_KERNEL(ctx, "nms_sparse_kernel(redo)", nms_sparse_kernel<<<grid, NS_THREADS, smem, ctx->stream>>>(
                 score, h, w, n, thr, border, slot0, ctx->nms_level, ctx->nms_flag, 2, k_cap, thr_bits, ctx->cand_keys, ctx->cand_count, any_redo));

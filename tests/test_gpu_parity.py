@@ -417,6 +417,34 @@ def test_batch_equals_single_and_is_deterministic():
     ctx.close()
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+def test_small_batch_two_stream_path_equals_serial(precision):
+    """Batches of one or two pairs run the raster chain (K1-K3) on a second stream with its own activation buffers, next
+    to the frame chain (api.cu, pose_batch_impl).  With the per-kernel event profile on, the same call stays on one
+    stream: both must give the same bits, call after call, in both precisions."""
+    blob = _trained_blob()
+    ground = synth.ground_texture(1024, seed=23, n_shapes=800)
+    pairs = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256) for s in range(2)]
+    ctx = Context(Config(max_batch=2, max_image_h=256, max_image_w=320, max_keypoints=512, precision=precision), weights=blob)
+    pe = PoseEstimator(ctx)
+    stack = lambda ps: (np.stack([p.frame for p in ps]), np.stack([p.tile for p in ps]), np.stack([p.dem for p in ps]),  # noqa: E731
+                        np.stack([p.k for p in ps]), np.stack([p.affine for p in ps]))
+    ctx.profile(True)
+    serial = pe.estimate_batch(*stack(pairs))
+    ctx.profile(False)
+    for _ in range(3):
+        both = pe.estimate_batch(*stack(pairs))
+        ones = [pe.estimate_batch(*stack([p]))[0] for p in pairs]
+        for i in range(2):
+            for got in (both[i], ones[i]):
+                assert got.status == serial[i].status == 0
+                assert (got.n_kp_qry, got.n_kp_ref, got.n_matches, got.n_inliers) == \
+                       (serial[i].n_kp_qry, serial[i].n_kp_ref, serial[i].n_matches, serial[i].n_inliers)
+                np.testing.assert_array_equal(got.r, serial[i].r)
+                np.testing.assert_array_equal(got.ecef, serial[i].ecef)
+    ctx.close()
+
+
 def test_two_live_contexts_do_not_share_state(rand_blob):
     """Tensor maps, repacked weights and workspaces belong to a context: two contexts with different
     weights used alternately must each reproduce their own single-context result."""
