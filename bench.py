@@ -728,7 +728,8 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
 
     def run(i):
         img, nb, c = mine[i]
-        tiles = np.stack([ground[gy * GRID: gy * GRID + TILE, gx * GRID: gx * GRID + TILE] for gx, gy in nb])
+        # views into the mosaic: estimate_candidates copies only the rasters the device cache does not hold
+        tiles = [ground[gy * GRID: gy * GRID + TILE, gx * GRID: gx * GRID + TILE] for gx, gy in nb]
         ids = np.array([gy * n_grid + gx for gx, gy in nb], np.int64)
         affs = np.stack([synth.tile_affine(gx * GRID, gy * GRID) for gx, gy in nb])
         best, res, hits = pe.estimate_candidates(img, tiles, ids, None, k, affs)

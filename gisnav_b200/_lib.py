@@ -87,6 +87,8 @@ SIGNATURES = {
     "gnb_pose_batch": (_I, [_VP, _I, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, C.POINTER(GnbPoseResult)]),
     "gnb_pose_from_records": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, C.POINTER(GnbPoseResult)]),
     "gnb_pose_candidates": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, C.POINTER(GnbPoseResult), C.POINTER(_I)]),
+    "gnb_pose_candidates_ptrs": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, C.POINTER(GnbPoseResult), C.POINTER(_I)]),
+    "gnb_cache_lookup": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "gnb_cache_clear": (_I, [_VP]),
     "gnb_rotate_crop": (_I, [_VP, _VP, _I, _VP, _I, _I, C.c_double, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "gnb_dense": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),

@@ -801,10 +801,101 @@ static void cache_copy(gnb_ctx* ctx, int entry, int slot, bool to_cache) {
     cp(ctx->c_mlogit + (size_t)entry * k, ctx->mlogit + (size_t)slot * k, k * sizeof(float));
 }
 
+// cache -> slots for all candidates of a call in ONE launch (the per-array cudaMemcpyAsync form above costs ~40 launches
+// per frame at 8 candidates).  Entry indices travel in the kernel parameters.
+#define GNB_GATHER_MAX 32
+struct CacheGather {
+    int n, sb;
+    int entry[GNB_GATHER_MAX];
+    int n_arr;
+    const char* c[5];      // cache arrays, [entry][bytes]
+    char* s[5];            // slot arrays,  [slot][bytes]
+    size_t bytes[5];
+};
+
+__global__ void __launch_bounds__(256) cache_gather_kernel(const CacheGather g) {
+    const int i = blockIdx.y;
+    for (int a = 0; a < g.n_arr; ++a) {
+        const size_t nb = g.bytes[a];
+        const char* src = g.c[a] + (size_t)g.entry[i] * nb;
+        char* dst = g.s[a] + (size_t)(g.sb + i) * nb;
+        if ((nb & 15) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb / 16; j += (size_t)gridDim.x * blockDim.x) d4[j] = s4[j];
+        } else {   // every array here is made of 4-byte words
+            const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+            uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+            for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb / 4; j += (size_t)gridDim.x * blockDim.x) d1[j] = s1[j];
+        }
+    }
+}
+
+static int cache_gather(gnb_ctx* ctx, const int* entry, int n, int sb) {
+    const size_t k = ctx->cfg.max_keypoints;
+    for (int i0 = 0; i0 < n; i0 += GNB_GATHER_MAX) {
+        CacheGather g;
+        g.n = n - i0 < GNB_GATHER_MAX ? n - i0 : GNB_GATHER_MAX;
+        g.sb = sb + i0;
+        for (int i = 0; i < g.n; ++i) g.entry[i] = entry[i0 + i];
+        int a = 0;
+        auto add = [&](const void* c, void* s_, size_t bytes) { g.c[a] = (const char*)c; g.s[a] = (char*)s_; g.bytes[a] = bytes; ++a; };
+        add(ctx->c_kp_xy, ctx->kp_xy, k * 2 * sizeof(float));
+        add(ctx->c_kp_count, ctx->kp_count, sizeof(int));
+        if (ctx->lg_state) {
+            add(ctx->c_desc, ctx->desc_f32, k * 256 * sizeof(float));
+        } else {
+            if (ctx->cfg.precision == 1) {
+                add(ctx->c_mproj_f32, ctx->mproj_f32, k * 256 * sizeof(float));
+                if (ctx->mproj_x3) add(ctx->c_mproj_x3, ctx->mproj_x3, k * 512 * sizeof(bf16));
+            } else
+                add(ctx->c_mproj, ctx->mproj, k * 256 * sizeof(bf16));
+            add(ctx->c_mlogit, ctx->mlogit, k * sizeof(float));
+        }
+        g.n_arr = a;
+        GNB_KERNEL(ctx, "cache_gather_kernel", cache_gather_kernel<<<dim3(16, g.n), 256, 0, ctx->stream>>>(g));
+    }
+    return GNB_OK;
+}
+
+// which of these rasters would be served from the cache by the next gnb_pose_candidates call with the same ids and size
+// (host-side lookup, nothing is modified): lets the caller skip gathering the pixels of cached rasters
+extern "C" int gnb_cache_lookup(gnb_ctx* ctx, const int64_t* tile_ids, int n_tiles, int ht, int wt, int* hit_out) {
+    if (!ctx || !tile_ids || !hit_out || n_tiles < 0) return GNB_E_INVALID;
+    std::vector<char> used(ctx->cache_cap, 0);
+    for (int i = 0; i < n_tiles; ++i) {
+        hit_out[i] = 0;
+        if (ctx->cache_h != ht || ctx->cache_w != wt || tile_ids[i] < 0) continue;
+        for (int e = 0; e < ctx->cache_cap; ++e)
+            if (ctx->cache_ids[e] == tile_ids[i] && !used[e]) { hit_out[i] = 1; used[e] = 1; break; }
+    }
+    return GNB_OK;
+}
+
+static int pose_candidates_impl(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* const* tile_ptrs, int ht,
+                                int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9, const double* affine12,
+                                gnb_pose_result* results, int* n_cache_hits);
+
 extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* tiles, int ht,
                                    int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9, const double* affine12,
                                    gnb_pose_result* results, int* n_cache_hits) {
     if (!ctx || !frame || !tiles || !k9 || !affine12 || !results || n_tiles < 1) return GNB_E_INVALID;
+    std::vector<const uint8_t*> ptrs(n_tiles);
+    for (int i = 0; i < n_tiles; ++i) ptrs[i] = tiles + (size_t)i * ht * wt;
+    return pose_candidates_impl(ctx, frame, hq, wq, n_tiles, ptrs.data(), ht, wt, tile_ids, dems, k9, affine12, results, n_cache_hits);
+}
+
+// same, one pointer per raster; the pointer of a raster the cache will serve (gnb_cache_lookup) may be NULL
+extern "C" int gnb_pose_candidates_ptrs(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* const* tile_ptrs,
+                                        int ht, int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9,
+                                        const double* affine12, gnb_pose_result* results, int* n_cache_hits) {
+    if (!ctx || !frame || !tile_ptrs || !k9 || !affine12 || !results || n_tiles < 1) return GNB_E_INVALID;
+    return pose_candidates_impl(ctx, frame, hq, wq, n_tiles, tile_ptrs, ht, wt, tile_ids, dems, k9, affine12, results, n_cache_hits);
+}
+
+static int pose_candidates_impl(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* const* tile_ptrs, int ht,
+                                   int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9, const double* affine12,
+                                   gnb_pose_result* results, int* n_cache_hits) {
     GNB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_tiles > ctx->cfg.max_batch) { GNB_SET_ERR(ctx, "n_tiles %d exceeds max_batch %d", n_tiles, ctx->cfg.max_batch); return GNB_E_CAPACITY; }
     const bool layers = ctx->lg_state != nullptr;
@@ -830,6 +921,11 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
             for (int e = 0; e < ctx->cache_cap; ++e)
                 if (ctx->cache_ids[e] == tile_ids[i] && !used[e]) { entry[i] = e; hit[i] = 1; used[e] = 1; ++hits; break; }
     }
+    for (int i = 0; i < n_tiles; ++i)
+        if (!hit[i] && !tile_ptrs[i]) {
+            GNB_SET_ERR(ctx, "raster %d is not in the feature cache: its pixels are required (gnb_cache_lookup)", i);
+            return GNB_E_INVALID;
+        }
     for (int i = 0; i < n_tiles; ++i) {
         if (entry[i] >= 0) continue;
         int best = -1;
@@ -859,7 +955,7 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
     const int m = (int)miss.size();
     if (m > 0) {
         for (int j = 0; j < m; ++j)
-            GNB_CUDA(ctx, cudaMemcpyAsync(cw.img_b + (size_t)j * ht * wt, tiles + (size_t)miss[j] * ht * wt, (size_t)ht * wt,
+            GNB_CUDA(ctx, cudaMemcpyAsync(cw.img_b + (size_t)j * ht * wt, tile_ptrs[miss[j]], (size_t)ht * wt,
                                           cudaMemcpyHostToDevice, ctx->stream));
         cw.img = cw.img_b;
         rc = gnb_conv_forward(ctx, m, ht, wt, 0);
@@ -870,7 +966,7 @@ extern "C" int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, i
         if (!layers && (rc = gnb_match_project(ctx, sb, m))) return rc;
         for (int j = 0; j < m; ++j) cache_copy(ctx, entry[miss[j]], sb + j, true);
     }
-    for (int i = 0; i < n_tiles; ++i) cache_copy(ctx, entry[i], sb + i, false);
+    if ((rc = cache_gather(ctx, entry.data(), n_tiles, sb))) return rc;
     GNB_CUDA(ctx, cudaGetLastError());
     int stride_a = 0;
     if (layers) {

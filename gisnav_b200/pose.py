@@ -145,20 +145,34 @@ class PoseEstimator:
                             affines: np.ndarray):
         """Candidate search (BASELINE config 4): one query frame against n reference rasters whose
         features are cached on the device by ``tile_ids`` (the reference caches the raster's features
-        per stamp, pose_node.py:226-241).  -> (index of the best candidate or None, results, cache hits)."""
+        per stamp, pose_node.py:226-241).  ``tiles``: u8 [n,ht,wt], or a LIST of n [ht,wt] arrays / views — then only the
+        rasters the cache does not hold are copied (a flyover re-uses its neighbours: no 8 MB gather per frame).
+        -> (index of the best candidate or None, results, cache hits)."""
         query = np.ascontiguousarray(query, np.uint8)
-        tiles = np.ascontiguousarray(tiles, np.uint8)
-        n, ht, wt = tiles.shape
         hq, wq = query.shape
         k = _k9(camera_info)
+        lazy = isinstance(tiles, (list, tuple))
+        n = len(tiles)
+        ht, wt = tiles[0].shape
         affines = np.ascontiguousarray(np.asarray(affines, np.float64).reshape(n, 12))
         ids = None if tile_ids is None else np.ascontiguousarray(np.asarray(tile_ids, np.int64).reshape(n))
         if dems is not None:
             dems = np.ascontiguousarray(dems, np.uint8).reshape(n, ht, wt)
         res = (_lib.GnbPoseResult * n)()
         hits = C.c_int(0)
-        self.ctx.check(self.ctx._lib.gnb_pose_candidates(self.ctx.handle, ptr(query), hq, wq, n, ptr(tiles), ht, wt, ptr(ids),
-                                                         ptr(dems), ptr(k), ptr(affines), res, C.byref(hits)))
+        if lazy:
+            # a list of (possibly strided) views: only the rasters the device cache does not hold are made contiguous
+            hit = np.zeros(n, np.int32)
+            if ids is not None:
+                self.ctx.check(self.ctx._lib.gnb_cache_lookup(self.ctx.handle, ptr(ids), n, ht, wt, ptr(hit)))
+            keep = [None if hit[i] else np.ascontiguousarray(tiles[i], np.uint8) for i in range(n)]
+            ptrs = (C.c_void_p * n)(*[None if t is None else t.ctypes.data for t in keep])
+            self.ctx.check(self.ctx._lib.gnb_pose_candidates_ptrs(self.ctx.handle, ptr(query), hq, wq, n, C.cast(ptrs, C.c_void_p), ht, wt,
+                                                                  ptr(ids), ptr(dems), ptr(k), ptr(affines), res, C.byref(hits)))
+        else:
+            tiles = np.ascontiguousarray(tiles, np.uint8)
+            self.ctx.check(self.ctx._lib.gnb_pose_candidates(self.ctx.handle, ptr(query), hq, wq, n, ptr(tiles), ht, wt, ptr(ids),
+                                                             ptr(dems), ptr(k), ptr(affines), res, C.byref(hits)))
         out = [_from_c(x) for x in res]
         ok = [i for i, r in enumerate(out) if r.ok]
         best = max(ok, key=lambda i: out[i].n_inliers) if ok else None

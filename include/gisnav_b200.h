@@ -190,6 +190,14 @@ int gnb_pose_from_records(gnb_ctx* ctx, const void* records, int n_records, int 
 int gnb_pose_candidates(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* tiles, int ht,
                         int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9, const double* affine12,
                         gnb_pose_result* results, int* n_cache_hits);
+/* The same with one HOST pointer per raster (u8 [ht,wt] each, contiguous).  The pointer of a raster that the cache will
+ * serve may be NULL: gnb_cache_lookup says which (hit_out[i] = 1), so the caller of a flyover stream gathers pixels only
+ * for the rasters that are new (pose_node.py:226-241 re-extracts a raster only when its stamp changes).  A NULL pointer for
+ * a raster that is NOT cached -> GNB_E_INVALID, nothing modified. */
+int gnb_pose_candidates_ptrs(gnb_ctx* ctx, const uint8_t* frame, int hq, int wq, int n_tiles, const uint8_t* const* tile_ptrs,
+                             int ht, int wt, const int64_t* tile_ids, const uint8_t* dems, const double* k9,
+                             const double* affine12, gnb_pose_result* results, int* n_cache_hits);
+int gnb_cache_lookup(gnb_ctx* ctx, const int64_t* tile_ids, int n_tiles, int ht, int wt, int* hit_out);
 int gnb_cache_clear(gnb_ctx* ctx);
 
 /* ---- the step in front of the path: StereoNode's rotate + centre-crop ------ */

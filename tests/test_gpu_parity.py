@@ -500,6 +500,48 @@ def test_candidate_search_with_tile_cache():
     ctx.close()
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+def test_candidate_search_lazy_rasters_equal_stacked(precision):
+    """estimate_candidates with a LIST of raster views: only rasters the device cache misses are copied (gnb_cache_lookup +
+    gnb_pose_candidates_ptrs with NULL for the cached ones); cached features reach their slots through one gather launch.
+    Same results as the stacked call on a second context, call after call; a NULL pointer for an uncached raster is refused."""
+    blob = _trained_blob()
+    ground = synth.ground_texture(2048, seed=26, n_shapes=3000)
+    mk = lambda: Context(Config(max_batch=4, max_image_h=256, max_image_w=320, max_keypoints=512, precision=precision), weights=blob)  # noqa: E731
+    ca, cb = mk(), mk()
+    pa, pb = PoseEstimator(ca), PoseEstimator(cb)
+    pairs = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256) for s in (1, 2, 3)]
+    big = np.concatenate([p.tile for p in pairs] + [synth.make_pair(ground, 14, frame_hw=(240, 320), tile_size=256).tile], axis=1)  # 256 x 1024
+    views = [big[:, 256 * i: 256 * (i + 1)] for i in range(4)]            # strided views, as cut from a mosaic
+    ids = np.array([7, 8, 9, 10])
+    for step, p in enumerate(pairs):
+        aff = np.stack([p.affine] * 4)
+        best_a, res_a, hits_a = pa.estimate_candidates(p.frame, views, ids, None, p.k, aff)
+        best_b, res_b, hits_b = pb.estimate_candidates(p.frame, np.stack(views), ids, None, p.k, aff)
+        assert best_a == best_b == step and hits_a == hits_b == (0 if step == 0 else 4)
+        for x, y in zip(res_a, res_b):
+            assert (x.status, x.n_matches, x.n_inliers) == (y.status, y.n_matches, y.n_inliers)
+            np.testing.assert_array_equal(x.r, y.r)
+            np.testing.assert_array_equal(x.ecef, y.ecef)
+    # an uncached raster without pixels is refused and leaves the cache as it was
+    hit = np.zeros(4, np.int32)
+    new_ids = np.array([7, 8, 99, 10], np.int64)
+    ca.check(ca._lib.gnb_cache_lookup(ca.handle, ptr(new_ids), 4, 256, 256, ptr(hit)))
+    assert hit.tolist() == [1, 1, 0, 1]
+    nulls = (C.c_void_p * 4)(None, None, None, None)
+    res = (_lib.GnbPoseResult * 4)()
+    p = pairs[0]
+    k9 = np.ascontiguousarray(p.k, np.float64)
+    aff = np.ascontiguousarray(np.stack([p.affine] * 4), np.float64)
+    frame = np.ascontiguousarray(p.frame)
+    rc = ca._lib.gnb_pose_candidates_ptrs(ca.handle, ptr(frame), 240, 320, 4, C.cast(nulls, C.c_void_p), 256, 256, ptr(new_ids), None,
+                                          ptr(k9), ptr(aff), res, None)
+    assert rc < 0 and "not in the feature cache" in ca._lib.gnb_last_error(ca.handle).decode()
+    _, _, hits = pa.estimate_candidates(p.frame, views, ids, None, p.k, aff)
+    assert hits == 4
+    ca.close(); cb.close()
+
+
 def test_device_resident_batch_and_config5_parameters():
     """estimate_batch_device (inputs already in HBM, the bench's `value` path) == estimate_batch (host
     buffers), at BASELINE config 5's parameters: keypoint cap 2048, 2000 RANSAC hypotheses."""
