@@ -46,7 +46,8 @@ PY
              ncu -i /tmp/k_$k.ncu-rep --page details > gpurun_out/ncu_${k}_details.txt 2>/dev/null
              ls -la gpurun_out/ncu_${k}_* ;;
   sanitizer) for tool in memcheck racecheck; do
-               timeout 1400 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "batch_equals_single or k2 or x3_layers" \
+               timeout 700 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+                 -k "batch_equals_single or two_stream or lazy_rasters or k2_keypoint or list_overflow or x3_layers" \
                  > gpurun_out/sanitizer_$tool.log 2>&1; tail -4 gpurun_out/sanitizer_$tool.log; done ;;
   stream)    timeout 1400 python bench.py --config 4 --steps 200 "$@" | tee gpurun_out/bench_config4.json ;;
   config5)   timeout 1400 python bench.py --config 5 --steps 4 "$@" | tee gpurun_out/bench_config5.json ;;
