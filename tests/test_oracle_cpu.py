@@ -377,6 +377,57 @@ def test_nms_survivors_above_a_level_depend_only_on_pixels_above_it():
             np.testing.assert_array_equal(np.where(full > level, full, 0), np.where(sparse > level, sparse, 0))
 
 
+def _list_nms_rounds(s, level, r=4):
+    """The algorithm of `nms_compact_kernel` + `nms_round_kernel<0,1,2>` (gisnav_b200/csrc/keypoints.cu) restated per listed
+    pixel in numpy: list = pixels >= level; round 0: a listed pixel is a maximum when no pixel of its clipped 9x9 window is
+    LARGER; its 9x9 block is ORed into SUPA and SUPB; round 1: unsuppressed-by-SUPA listed pixels with no larger pixel that
+    is itself unsuppressed (SUPA) -> maxima, blocks ORed into SUPB; round 2: the same against SUPB.  Maxima are final."""
+    h, w = s.shape
+    ys, xs = np.nonzero(s >= level)
+    sup_a = np.zeros((h, w), bool)
+    sup_b = np.zeros((h, w), bool)
+    out = np.zeros((h, w), bool)
+
+    def round_(read, writes):
+        found = []
+        for y, x in zip(ys.tolist(), xs.tolist()):
+            if read is not None and read[y, x]:
+                continue
+            y0, y1, x0, x1 = max(y - r, 0), min(y + r, h - 1) + 1, max(x - r, 0), min(x + r, w - 1) + 1
+            win = s[y0:y1, x0:x1]
+            larger = win > s[y, x]
+            if read is not None:
+                larger &= ~read[y0:y1, x0:x1]
+            if not larger.any():
+                found.append((y, x, y0, y1, x0, x1))
+        for y, x, y0, y1, x0, x1 in found:       # the kernel ORs while it runs, but never into the bitmap it reads
+            out[y, x] = True
+            for m in writes:
+                m[y0:y1, x0:x1] = True
+
+    round_(None, (sup_a, sup_b))
+    round_(sup_a, (sup_b,))
+    round_(sup_b, ())
+    return out
+
+
+def test_list_based_nms_rounds_equal_simple_nms_above_the_level():
+    """CPU statement of the product NMS (lists over the whole image): its maxima are exactly the survivors of simple_nms
+    at or above the level — random maps, heavy ties, a plateau, maxima on the image border."""
+    rng = np.random.default_rng(31)
+    for trial in range(5):
+        if trial % 2 == 0:
+            s = (rng.random((72, 90)).astype(np.float32) ** 3)
+        else:
+            s = (np.round(rng.random((64, 80)) * 10) / 10).astype(np.float32)
+            s[10:18, 30:44] = 0.7
+        s[0, 5] = s[-1, -1] = s[20, 0] = 1.5                                    # border maxima (clipped windows)
+        full = nms_ref.simple_nms(s, 4) > 0
+        for level in (np.float32(0.05), np.float32(0.35), np.float32(0.7)):
+            got = _list_nms_rounds(s, level)
+            np.testing.assert_array_equal(got, full & (s >= level))
+
+
 def test_topk_selection_is_unchanged_by_zeroing_below_a_safe_level():
     """End-to-end form of the lemma: if at least K survivors lie above level T, the ordered top-K keypoint list is the
     same whether or not the pixels <= T are zeroed first — the acceptance test of a sparse, top-K-aware NMS."""
