@@ -14,8 +14,20 @@
 
 // ------------------------------------------------------------------------------------------------
 // conv1a, fp32: same tiling as conv1a_kernel (conv.cu).  Output pixel = 128 bf16: hi[64] then lo[64].
+// The kernel is issue-bound (ncu: issue slots 73 % busy, DRAM 60 %; under the power cap of the fp32-faithful step the SM clock
+// drops to ~1.6 GHz and an issue-bound kernel slows with it), so the arithmetic uses Blackwell's packed fp32 pairs — FFMA2 /
+// FADD2 (`fma.rn.f32x2`, `add.rn.f32x2`): two IEEE fp32 operations per issue slot, bit-identical to the scalar form; the
+// pixel value is a broadcast operand (`FFMA2 R, Rv.F32, Rw.F32x2.HI_LO, Racc`).  Measured per 128 frames: 7.79 -> 7.31 ms.
+// A variant with eight channels per lane (16-byte stores, 124 registers, two CTAs per SM) was slower: 8.82 ms.
 #define X1_TH 8
 #define X1_TW 32
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 __global__ void __launch_bounds__(256, 4) conv1a_x3_kernel(const uint8_t* __restrict__ img, const float* __restrict__ wt,
                                                            const float* __restrict__ bias, int h, int w, bf16* __restrict__ out) {
     __shared__ float patch[X1_TH + 2][X1_TW + 2 + 2];
@@ -28,17 +40,18 @@ __global__ void __launch_bounds__(256, 4) conv1a_x3_kernel(const uint8_t* __rest
         if (y >= 0 && y < h && x >= 0 && x < w) f = __fdiv_rn((float)im[(size_t)y * w + x], 255.0f);
         patch[ly][lx] = f;
     }
-    // lane l owns channels [4 (l % 16), +4) of pixel (l / 16) of a 2-pixel group: its 36 weights live in registers (four
-    // CTAs per SM), and the 16 lanes of a pixel write its 128-byte hi block and its 128-byte lo block with one 8-byte store each
+    // lane l owns channels [4 (l % 16), +4) of pixel (l / 16) of a 2-pixel group: its 36 weights live in registers as 18
+    // pairs (four CTAs per SM), and the 16 lanes of a pixel write its 128-byte hi block and its 128-byte lo block with one
+    // 8-byte store each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = (lane & 15) * 4, sub = lane >> 4;
-    float wr[9][4], br[4];
+    f32x2 wr[9][2], br[2];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) wr[t][j] = wt[t * 64 + c0 + j];   // w_f32 [tap][cout_pad = 64][cin = 1]
+        for (int j = 0; j < 2; ++j) wr[t][j] = f2_pack(wt[t * 64 + c0 + 2 * j], wt[t * 64 + c0 + 2 * j + 1]);   // w_f32 [tap][cout_pad = 64][cin = 1]
 #pragma unroll
-    for (int j = 0; j < 4; ++j) br[j] = bias[c0 + j];
+    for (int j = 0; j < 2; ++j) br[j] = f2_pack(bias[c0 + 2 * j], bias[c0 + 2 * j + 1]);
     __syncthreads();
     const int ly = warp, y = y0 + ly;
     if (y >= h) return;
@@ -48,21 +61,26 @@ __global__ void __launch_bounds__(256, 4) conv1a_x3_kernel(const uint8_t* __rest
         float v[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) v[t] = patch[ly + t / 3][lx + t % 3];
-        float a[4];
+        uint32_t hi[2], lo[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc = 0.f;
+        for (int j = 0; j < 2; ++j) {
+            f32x2 acc = f2_pack(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wr[t][j], acc);
-            a[j] = fmaxf(acc + br[j], 0.f);
+            for (int t = 0; t < 9; ++t) acc = f2_fma(f2_pack(v[t], v[t]), wr[t][j], acc);   // same chain per channel as the scalar form
+            float a0, a1;
+            f2_unpack(f2_add(acc, br[j]), a0, a1);
+            a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+            float r0, r1;
+            f2_unpack(f2_sub(f2_pack(a0, a1), f2_pack(__low2float(hh), __high2float(hh))), r0, r1);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
-        const __nv_bfloat162 l0 = __floats2bfloat162_rn(__fsub_rn(a[0], __low2float(h0)), __fsub_rn(a[1], __high2float(h0)));
-        const __nv_bfloat162 l1 = __floats2bfloat162_rn(__fsub_rn(a[2], __low2float(h1)), __fsub_rn(a[3], __high2float(h1)));
         if (x < w) {
             bf16* o = out + ((size_t)b * h * w + (size_t)y * w + x) * 128 + c0;
-            *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-            *reinterpret_cast<uint2*>(o + 64) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            *reinterpret_cast<uint2*>(o) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(o + 64) = make_uint2(lo[0], lo[1]);
         }
     }
 }
