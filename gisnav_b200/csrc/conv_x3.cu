@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(256) gemm256_f32_kernel(const void* __restrict
     __shared__ float Ws[32][64 + 4];   // [k][n]
     const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    float acc[4][4];
+    f32x2 acc[4][2];   // packed pairs along n: FFMA2 halves the issue slots of the inner loop, same fp32 chain per output
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 2; ++j) acc[i][j] = f2_pack(0.f, 0.f);
     // loader mapping: thread -> (row r = tid / 4, 8 consecutive k = (tid % 4) * 8)
     const int lr = tid >> 2, lk = (tid & 3) * 8;
     int src = -1;
@@ -152,21 +152,25 @@ __global__ void __launch_bounds__(256) gemm256_f32_kernel(const void* __restrict
         for (int k = 0; k < 32; ++k) {
             const float4 x = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
             const float4 y = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
-            const float xa[4] = {x.x, x.y, x.z, x.w}, yb[4] = {y.x, y.y, y.z, y.w};
+            const float xa[4] = {x.x, x.y, x.z, x.w};
+            const f32x2 yb[2] = {f2_pack(y.x, y.y), f2_pack(y.z, y.w)};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], yb[j], acc[i][j]);
+                for (int j = 0; j < 2; ++j) acc[i][j] = f2_fma(f2_pack(xa[i], xa[i]), yb[j], acc[i][j]);
         }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
         if (m >= m_rows) continue;
+        float r[4];
+        f2_unpack(acc[i][0], r[0], r[1]);
+        f2_unpack(acc[i][1], r[2], r[3]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < n_cols) c[(size_t)m * ldc + n] = __fmul_rn(__fadd_rn(acc[i][j], bias[n]), scale);
+            if (n < n_cols) c[(size_t)m * ldc + n] = __fmul_rn(__fadd_rn(r[j], bias[n]), scale);
         }
     }
 }
