@@ -720,13 +720,16 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
         nb.sort(key=lambda g: (g[0] * GRID + TILE / 2 - c[0]) ** 2 + (g[1] * GRID + TILE / 2 - c[1]) ** 2)
         mine.append((img, nb[:8], c))
     precision = 0 if args.precision == "bf16_fast" else 1
-    ctx = gisnav_b200.Context(gisnav_b200.Config(max_batch=8, max_image_h=1024, max_image_w=1280, tile_cache=48, precision=precision,
-                                                 max_keypoints=args.keypoints or cfg["keypoints"], ransac_iters=args.ransac_iters or cfg["iters"]),
-                              device=local, weights_device_ptr=wt.data_ptr(), weights_nbytes=W.BLOB_BYTES)
-    pe = gisnav_b200.PoseEstimator(ctx)
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    # frames are independent: `inflight` contexts per GPU (own stream, workspace and tile cache), one host thread each, take
+    # the frames of this rank in turn — host work and the short kernels of one frame overlap with the other frame's
+    inflight = max(1, args.inflight)
+    ctxs = [gisnav_b200.Context(gisnav_b200.Config(max_batch=8, max_image_h=1024, max_image_w=1280, tile_cache=48, precision=precision,
+                                                   max_keypoints=args.keypoints or cfg["keypoints"], ransac_iters=args.ransac_iters or cfg["iters"]),
+                                device=local, weights_device_ptr=wt.data_ptr(), weights_nbytes=W.BLOB_BYTES) for _ in range(inflight)]
+    pes = [gisnav_b200.PoseEstimator(c) for c in ctxs]
+    streams = [torch.cuda.ExternalStream(c.stream_ptr, device=dev) for c in ctxs]
 
-    def run(i):
+    def run(i, pe):
         img, nb, c = mine[i]
         # views into the mosaic: estimate_candidates copies only the rasters the device cache does not hold
         tiles = [ground[gy * GRID: gy * GRID + TILE, gx * GRID: gx * GRID + TILE] for gx, gy in nb]
@@ -740,28 +743,49 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
             err = float(np.hypot(cc[0] + gx * GRID - c[0], cc[1] + gy * GRID - c[1]))
         return best, hits, err
 
+    def run_range(lo, hi):
+        """frames [lo, hi) of this rank, dealt over the in-flight contexts; results in frame order"""
+        rows = [None] * (hi - lo)
+
+        def worker(j):
+            for i in range(lo + j, hi, inflight):
+                rows[i - lo] = run(i, pes[j])
+
+        if inflight == 1:
+            worker(0)
+        else:
+            ts = [threading.Thread(target=worker, args=(j,)) for j in range(inflight)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        return rows
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        run(i)
+    for j in range(inflight):          # every context sees the warm-up frames (and caches their rasters)
+        for i in range(args.warmup):
+            run(i, pes[j])
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = ctx.launch_count
+    l0 = sum(c.launch_count for c in ctxs)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ctxs]
+    for (e0, _), st in zip(ev, streams):
+        e0.record(st)
     t0 = time.perf_counter()
-    rows = [run(i) for i in range(args.warmup, args.warmup + args.steps)]
-    e1.record(stream)
+    rows = run_range(args.warmup, args.warmup + args.steps)
+    for (_, e1), st in zip(ev, streams):
+        e1.record(st)
     barrier()
     wall = time.perf_counter() - t0
     # the stream is host-driven (tile gathering, cache bookkeeping): take the larger of device and host time, max over ranks
-    ms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([sum(r[0] is not None for r in rows), sum(r[1] for r in rows), len(rows), ctx.launch_count - l0,
+    ms = torch.tensor([max(max(e0.elapsed_time(e1) for e0, e1 in ev), wall * 1e3)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([sum(r[0] is not None for r in rows), sum(r[1] for r in rows), len(rows), sum(c.launch_count for c in ctxs) - l0,
                         sum(r[2] ** 2 for r in rows if r[2] is not None), sum(r[2] is not None for r in rows)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -774,7 +798,7 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
             "metric": "localised_frames_per_sec (8 candidate pairs per frame)", "value": loc / secs, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16" if precision == 0 else "bf16x3+f32", "data": "synthetic flyover (procedural texture, trained-from-scratch weights)",
-            "config": workload_config(args, cfg),
+            "config": dict(workload_config(args, cfg), frames_in_flight_per_gpu=inflight),
             "e2e": {"value": loc / secs, "unit": "frames/s", "h2d_bytes_per_step": h * w + 8 * (1 - hits / (8.0 * frames)) * TILE * TILE,
                     "d2h_bytes_per_step": 8 * 200, "note": "host buffers in, host results out: value is the end-to-end number"},
             "candidate_pairs_per_sec": 8 * frames / secs, "cache_hit_rate": hits / (8.0 * frames), "frames": int(frames),
@@ -782,7 +806,8 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -798,6 +823,7 @@ def main():
     ap.add_argument("--precision", default="both", choices=["both", "fp32_faithful", "bf16_fast"],
                     help="both (default): headline = fp32-faithful mode, the bf16 fast mode measured in the same run under `bf16_fast`")
     ap.add_argument("--batch", type=int, default=0, help="override pairs per step per GPU (weak-scaling configs)")
+    ap.add_argument("--inflight", type=int, default=4, help="config 4: frames in flight per GPU (contexts + host threads)")
     ap.add_argument("--keypoints", type=int, default=0, help="override the config's keypoint cap")
     ap.add_argument("--ransac-iters", type=int, default=0, help="override the config's hypothesis count")
     ap.add_argument("--matcher-layers", type=int, default=0,
