@@ -13,7 +13,8 @@ BASELINE.json configs:
      pose_node.py:191-205): throughput at batch 1 = 1 / latency
   3  batch of 64 such pairs per step, K = 1024 (DEFAULT: the largest single-GPU configuration)
   4  synthetic flyover stream, 8 candidate rasters per frame, device tile-feature cache, frames dealt round-robin
-     over the GPUs (metric: frames/s localised; a step = one frame per GPU)
+     over the GPUs and, on a GPU, over --inflight contexts with one host thread each (metric: frames/s localised;
+     a step = one frame per GPU)
   5  512 pairs per step in total (512 / N per GPU: STRONG scaling), K = 2048, 2000 RANSAC hypotheses
 
 A step = one pass of the hot path (extract x2 + match + PnP/RANSAC + WGS84 tail) over one batch.  `value` =
@@ -23,7 +24,7 @@ matched pairs/s (status OK: >= 15 matches and PnP success, pose_node.py:63,299-3
 Arithmetic.  The headline (`value`, `e2e`, `roofline`) is the fp32-FAITHFUL mode (`Config(precision=1)`: split-bf16
 tensor-core operands, three MMAs per product, fp32 accumulation, fp32 heads and matcher) because the reference's
 tensors are fp32 (pose_node.py:254-287); the bf16 fast mode is measured in the same run and reported under
-`fast_mode`.  `accuracy` compares BOTH modes with the plain fp32 CPU network on the same pairs.
+`bf16_fast`.  `accuracy_vs_fp32` compares BOTH modes with the plain fp32 CPU network on the same pairs.
 Pairs are independent, so N GPUs run N disjoint shards with no data-path collective; the only collective is the
 NCCL broadcast of the weight blob at start-up.
 """
