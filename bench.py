@@ -724,10 +724,11 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
     # frames are independent: `inflight` contexts per GPU (own stream, workspace and tile cache), one host thread each, take
     # the frames of this rank in turn — host work and the short kernels of one frame overlap with the other frame's
     inflight = max(1, args.inflight)
-    ctxs = [gisnav_b200.Context(gisnav_b200.Config(max_batch=8, max_image_h=1024, max_image_w=1280, tile_cache=48, precision=precision,
-                                                   max_keypoints=args.keypoints or cfg["keypoints"], ransac_iters=args.ransac_iters or cfg["iters"]),
-                                device=local, weights_device_ptr=wt.data_ptr(), weights_nbytes=W.BLOB_BYTES) for _ in range(inflight)]
-    pes = [gisnav_b200.PoseEstimator(c) for c in ctxs]
+    fs = gisnav_b200.FrameStream(inflight, gisnav_b200.Config(max_batch=8, max_image_h=1024, max_image_w=1280, tile_cache=48, precision=precision,
+                                                              max_keypoints=args.keypoints or cfg["keypoints"],
+                                                              ransac_iters=args.ransac_iters or cfg["iters"]),
+                                 device=local, weights_device_ptr=wt.data_ptr(), weights_nbytes=W.BLOB_BYTES)
+    ctxs = fs.contexts
     streams = [torch.cuda.ExternalStream(c.stream_ptr, device=dev) for c in ctxs]
 
     def run(i, pe):
@@ -745,35 +746,19 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
         return best, hits, err
 
     def run_range(lo, hi):
-        """frames [lo, hi) of this rank, dealt over the in-flight contexts; results in frame order"""
-        rows = [None] * (hi - lo)
-
-        def worker(j):
-            for i in range(lo + j, hi, inflight):
-                rows[i - lo] = run(i, pes[j])
-
-        if inflight == 1:
-            worker(0)
-        else:
-            ts = [threading.Thread(target=worker, args=(j,)) for j in range(inflight)]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-        return rows
+        """frames [lo, hi) of this rank through the in-flight contexts (gisnav_b200/stream.py); results in frame order"""
+        return fs.map_frames([(lambda pe, i=i: run(i, pe)) for i in range(lo, hi)])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for j in range(inflight):          # every context sees the warm-up frames (and caches their rasters)
-        for i in range(args.warmup):
-            run(i, pes[j])
+    fs.for_each_context(lambda pe: [run(i, pe) for i in range(args.warmup)])   # every context sees the warm-up frames (and caches their rasters)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = sum(c.launch_count for c in ctxs)
+    l0 = fs.launch_count
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ctxs]
     for (e0, _), st in zip(ev, streams):
@@ -786,7 +771,7 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
     wall = time.perf_counter() - t0
     # the stream is host-driven (tile gathering, cache bookkeeping): take the larger of device and host time, max over ranks
     ms = torch.tensor([max(max(e0.elapsed_time(e1) for e0, e1 in ev), wall * 1e3)], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([sum(r[0] is not None for r in rows), sum(r[1] for r in rows), len(rows), sum(c.launch_count for c in ctxs) - l0,
+    cnt = torch.tensor([sum(r[0] is not None for r in rows), sum(r[1] for r in rows), len(rows), fs.launch_count - l0,
                         sum(r[2] ** 2 for r in rows if r[2] is not None), sum(r[2] is not None for r in rows)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -807,8 +792,7 @@ def run_stream(args, cfg, rank, world, local, dev, wt):
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    for c in ctxs:
-        c.close()
+    fs.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

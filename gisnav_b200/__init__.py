@@ -11,5 +11,6 @@ from .keypoint_record import KEYPOINT_DTYPE, KEYPOINT_DTYPE_256  # noqa: F401
 from .matcher import BruteForceRatioMatcher, KeypointMatcher  # noqa: F401
 from .pose import PoseEstimator, PoseResult, compute_pose  # noqa: F401
 from .stereo import StereoAligner  # noqa: F401
+from .stream import FrameStream  # noqa: F401
 
 __version__ = "0.1.0"

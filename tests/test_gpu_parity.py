@@ -542,6 +542,42 @@ def test_candidate_search_lazy_rasters_equal_stacked(precision):
     ca.close(); cb.close()
 
 
+def test_frame_stream_keeps_order_and_equals_one_context():
+    """FrameStream (gisnav_b200/stream.py): three contexts, one host thread each, frames handed out dynamically — the results
+    come back in submission order and are bit-identical to the same frames through ONE context, whatever context served
+    a frame and whatever its raster cache held; an exception inside a job surfaces through its future."""
+    from gisnav_b200 import FrameStream
+
+    blob = _trained_blob()
+    ground = synth.ground_texture(2048, seed=27, n_shapes=3000)
+    pairs = [synth.make_pair(ground, s, frame_hw=(240, 320), tile_size=256) for s in range(6)]
+    decoy = synth.make_pair(ground, 17, frame_hw=(240, 320), tile_size=256).tile
+    cfg = Config(max_batch=2, max_image_h=256, max_image_w=320, max_keypoints=512)
+
+    def job(p, idx):
+        def run(pe):
+            best, res, _ = pe.estimate_candidates(p.frame, [decoy, p.tile], np.array([1000, idx]), None, p.k, np.stack([p.affine] * 2))
+            return best, res[1]
+        return run
+
+    one = Context(cfg, weights=blob)
+    want = [job(p, i)(PoseEstimator(one)) for i, p in enumerate(pairs)]
+    one.close()
+    with FrameStream(3, cfg, weights=blob) as fs:
+        for _ in range(2):      # second round: every raster is cached in SOME context, not necessarily the serving one
+            got = fs.map_frames([job(p, i) for i, p in enumerate(pairs)])
+            for (b0, r0), (b1, r1) in zip(want, got):
+                assert b0 == b1 == 1 and (r0.n_matches, r0.n_inliers) == (r1.n_matches, r1.n_inliers)
+                np.testing.assert_array_equal(r0.r, r1.r)
+                np.testing.assert_array_equal(r0.ecef, r1.ecef)
+        assert fs.launch_count > 0
+        bad = fs.submit(lambda pe: pe.estimate_candidates(pairs[0].frame[:100, :100], [decoy], None, None, pairs[0].k, pairs[0].affine[None]))
+        with pytest.raises(Exception):
+            bad.result()
+        ok = fs.submit(job(pairs[0], 0)).result()          # the stream still serves after a failed job
+        assert ok[0] == 1
+
+
 def test_device_resident_batch_and_config5_parameters():
     """estimate_batch_device (inputs already in HBM, the bench's `value` path) == estimate_batch (host
     buffers), at BASELINE config 5's parameters: keypoint cap 2048, 2000 RANSAC hypotheses."""
